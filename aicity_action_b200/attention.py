@@ -1,0 +1,265 @@
+"""Drop-in for slowfast/models/attention.py: attention_pool, MultiScaleAttention, MultiScaleBlock.
+
+Same constructor signatures, attribute names, parameter names / shapes / registration order and
+`forward(x, thw_shape) -> (tensor, thw)` contract as the reference (attention.py:12, 86, 287), so
+`state_dict()` interchanges with reference checkpoints.  The nn.Linear /
+nn.Conv3d / nn.LayerNorm sub-modules are *parameter holders only*: all arithmetic is issued to the
+sm_100a kernels of libmvit_b200.so through `ops` (no torch math on the hot path, no CPU fallback).
+
+Dataflow of one block (B200 form of SURVEY.md §3.3; ✚ marks fusions that remove reference kernels):
+    LN(1e-6) -> qkv GEMM(+bias) -> pool_{q,k,v}: depthwise conv3d ✚ LN(1e-5), read straight from the
+    [B,N,3,h,96] GEMM output (no channels-first copies) -> fused attention softmax(qkᵀ/√d)v ✚ +q ✚
+    head-merge -> proj GEMM ✚ bias ✚ skip-residual ✚ DropPath scale -> LN -> fc1 GEMM ✚ bias ✚ GELU ->
+    fc2 GEMM ✚ bias ✚ residual ✚ DropPath scale.  Identity MaxPool3d([1,1,1]) skips are elided (D6).
+"""
+from __future__ import annotations
+
+import numpy
+import torch
+import torch.nn as nn
+
+from . import ops
+from .common import DropPath, Mlp, drop_path_scale
+from .weights import cached_weight
+
+
+def _compute_dtype(x: torch.Tensor) -> torch.dtype:
+    """fp32 tensors run the fp32 kernels unless a bf16 autocast region is active (the reference's
+    TRAIN.MIXED_PRECISION / torch.autocast contract); bf16 tensors run the tensor-core kernels."""
+    if x.dtype == torch.bfloat16:
+        return torch.bfloat16
+    if x.dtype == torch.float32:
+        if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
+    raise TypeError(f"unsupported activation dtype {x.dtype} (float32 or bfloat16)")
+
+
+def _no_grad_only(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "aicity_action_b200: backward kernels are not part of this build; run under torch.no_grad()")
+
+
+def _pool_desc(pool):
+    """(mode, kernel, stride, weight) of a reference-style pool module, or None."""
+    if pool is None:
+        return None
+    t3 = lambda v: [int(v)] * 3 if isinstance(v, int) else [int(a) for a in v]
+    if isinstance(pool, nn.Conv3d):
+        k, s, p = t3(pool.kernel_size), t3(pool.stride), t3(pool.padding)
+        if pool.groups != pool.in_channels or pool.in_channels != pool.out_channels or pool.bias is not None:
+            raise NotImplementedError("attention_pool: only depthwise bias-free Conv3d pooling is supported")
+        mode, w = "conv", pool.weight
+    elif isinstance(pool, nn.MaxPool3d):
+        k, s, p = t3(pool.kernel_size), t3(pool.stride), t3(pool.padding)
+        if pool.ceil_mode:
+            raise NotImplementedError("attention_pool: ceil_mode=True is not supported")
+        mode, w = "max", None
+    elif isinstance(pool, nn.AvgPool3d):
+        k, s, p = t3(pool.kernel_size), t3(pool.stride), t3(pool.padding)
+        if pool.ceil_mode or not pool.count_include_pad:
+            raise NotImplementedError("attention_pool: AvgPool3d variant not supported")
+        mode, w = "avg", None
+    else:
+        raise NotImplementedError(f"attention_pool: unsupported pool module {type(pool).__name__}")
+    if p != [x // 2 for x in k]:
+        raise NotImplementedError("attention_pool: padding must be kernel//2 (as built by the reference)")
+    return mode, k, s, w
+
+
+def attention_pool(tensor, pool, thw_shape, has_cls_embed=True, norm=None, pool2d=None):
+    """attention.py:12-83.  tensor: [B, heads, L, d] (any strides with unit channel stride, e.g. a
+    slice of the qkv output) or [B, L, C]; returns (pooled tensor, [T', H', W'])."""
+    if pool is None:
+        return tensor, thw_shape
+    if pool2d is not None:
+        raise NotImplementedError("pool2d (the reference's ONNX/TNN export aid) is not supported")
+    _no_grad_only(tensor)
+    desc = _pool_desc(pool)
+    mode, k, s, w = desc
+    ln = None
+    if norm is not None:
+        ln = (norm.weight, norm.bias, norm.eps)
+    if tensor.ndim == 4:
+        if tensor.stride(3) != 1:
+            tensor = tensor.contiguous()
+        out, thw = ops.attention_pool_heads(tensor, list(thw_shape), k, s, mode=mode, weight=w, ln=ln,
+                                            has_cls=has_cls_embed)
+        return out, thw
+    if tensor.ndim == 3:
+        if ln is None and mode != "conv":
+            out, thw = ops.attention_pool_tokens(tensor, list(thw_shape), k, s, mode=mode, has_cls=has_cls_embed)
+            return out, thw
+        out, thw = ops.attention_pool_heads(tensor.unsqueeze(1), list(thw_shape), k, s, mode=mode, weight=w,
+                                            ln=ln, has_cls=has_cls_embed)
+        return out.squeeze(1), thw
+    raise NotImplementedError(f"Unsupported input dimension {tensor.shape}")
+
+
+class MultiScaleAttention(nn.Module):
+    """attention.py:86-284."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, drop_rate=0.0, kernel_q=(1, 1, 1),
+                 kernel_kv=(1, 1, 1), stride_q=(1, 1, 1), stride_kv=(1, 1, 1), norm_layer=nn.LayerNorm,
+                 has_cls_embed=True, mode="conv", pool_first=False, use_query_residual_pool=False,
+                 expand_channel=False, expand_to_dim=None):
+        super().__init__()
+        self.drop_rate = drop_rate
+        self.num_heads = num_heads
+        dim_out = expand_to_dim if expand_channel else dim
+        self.dim_out = dim_out
+        head_dim = dim_out // num_heads
+        self.scale = head_dim ** -0.5
+        self.has_cls_embed = has_cls_embed
+        pad_q = [int(q // 2) for q in kernel_q]
+        pad_kv = [int(kv // 2) for kv in kernel_kv]
+
+        self.qkv = nn.Linear(dim, dim_out * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim_out, dim_out)
+        if drop_rate > 0.0:
+            self.proj_drop = nn.Dropout(drop_rate)
+
+        # kernel (1,1,1) with stride (1,1,1) means "no pooling" (attention.py:131-134)
+        if numpy.prod(kernel_q) == 1 and numpy.prod(stride_q) == 1:
+            kernel_q = ()
+        if numpy.prod(kernel_kv) == 1 and numpy.prod(stride_kv) == 1:
+            kernel_kv = ()
+
+        def make(kind, kernel, stride, pad):
+            if len(kernel) == 0:
+                return None
+            if kind == "conv":
+                return nn.Conv3d(head_dim, head_dim, kernel, stride=stride, padding=pad, groups=head_dim,
+                                 bias=False)
+            cls = nn.AvgPool3d if kind == "avg" else nn.MaxPool3d
+            return cls(kernel, stride, pad, ceil_mode=False)
+
+        if mode in ("avg", "max"):
+            self.pool_q = make(mode, kernel_q, stride_q, pad_q)
+            self.pool_k = make(mode, kernel_kv, stride_kv, pad_kv)
+            self.pool_v = make(mode, kernel_kv, stride_kv, pad_kv)
+        elif mode == "conv":
+            self.pool_q = make("conv", kernel_q, stride_q, pad_q)
+            self.norm_q = norm_layer(head_dim) if len(kernel_q) > 0 else None
+            self.pool_k = make("conv", kernel_kv, stride_kv, pad_kv)
+            self.norm_k = norm_layer(head_dim) if len(kernel_kv) > 0 else None
+            self.pool_v = make("conv", kernel_kv, stride_kv, pad_kv)
+            self.norm_v = norm_layer(head_dim) if len(kernel_kv) > 0 else None
+        else:
+            raise NotImplementedError(f"Unsupported model {mode}")
+        self.use_query_residual_pool = use_query_residual_pool
+
+    # -- B200 forward ----------------------------------------------------------------------
+    def _pooled(self, qkv5, which, pool, norm, thw_shape):
+        """qkv5: [B, N, 3, h, d] GEMM output; returns contiguous [B, h, L', d] for q/k/v #which."""
+        t = qkv5[:, :, which].permute(0, 2, 1, 3)          # [B, h, N, d] strided view, no copy
+        if pool is None:
+            # un-pooled operand: the head-major gather the attention kernel needs is a 1x1x1 "avg" pool
+            out, _ = ops.attention_pool_heads(t, [1, 1, t.shape[2]], [1, 1, 1], [1, 1, 1], mode="avg")
+            return out, list(thw_shape)
+        return attention_pool(t, pool, thw_shape, has_cls_embed=self.has_cls_embed, norm=norm)
+
+    def attend(self, x, thw_shape):
+        """Everything before `proj`: returns (y [B, Lq, C], out_thw) with y = softmax(qkᵀ·scale)v (+q)."""
+        B, N, _ = x.shape
+        C, h = self.dim_out, self.num_heads
+        qkv = ops.linear(x, cached_weight(self.qkv.weight, x.dtype), self.qkv.bias)
+        qkv5 = qkv.view(B, N, 3, h, C // h)
+        q, out_shape = self._pooled(qkv5, 0, self.pool_q, getattr(self, "norm_q", None), thw_shape)
+        k, _ = self._pooled(qkv5, 1, self.pool_k, getattr(self, "norm_k", None), thw_shape)
+        v, _ = self._pooled(qkv5, 2, self.pool_v, getattr(self, "norm_v", None), thw_shape)
+        y = ops.attention(q, k, v, self.scale, self.use_query_residual_pool)
+        return y, out_shape
+
+    def forward(self, x, thw_shape, residual=None, row_scale=None):
+        """Reference contract: (x [B,N,dim], thw) -> (proj(attn) [B,Lq,dim_out], thw').
+        `residual` / `row_scale` (used by MultiScaleBlock) fold `x_res + drop_path(.)` into the proj GEMM."""
+        _no_grad_only(x)
+        if self.drop_rate > 0.0 and self.training:
+            raise NotImplementedError("proj dropout in training is not supported by the B200 path yet")
+        dt = _compute_dtype(x)
+        y, out_shape = self.attend(x.to(dt), thw_shape)
+        out = ops.linear(y, cached_weight(self.proj.weight, dt), self.proj.bias, residual=residual,
+                         row_scale=row_scale)
+        return out, out_shape
+
+
+class MultiScaleBlock(nn.Module):
+    """attention.py:287-446."""
+
+    def __init__(self, dim, dim_out, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_scale=None, drop_rate=0.0,
+                 drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, up_rate=None,
+                 kernel_q=(1, 1, 1), kernel_kv=(1, 1, 1), stride_q=(1, 1, 1), stride_kv=(1, 1, 1),
+                 mode="conv", has_cls_embed=True, pool_first=False, use_query_residual_pool=False,
+                 channel_expand_front=False, pool_skip_use_conv=False):
+        super().__init__()
+        self.dim = dim
+        self.dim_out = dim_out
+        self.norm1 = norm_layer(dim)
+        kernel_skip = [s + 1 if s > 1 else s for s in stride_q]
+        stride_skip = stride_q
+        padding_skip = [int(skip // 2) for skip in kernel_skip]
+
+        dim_in = dim
+        self.expand_channel = bool(channel_expand_front and dim != dim_out)
+        self.pool_skip_use_conv = pool_skip_use_conv
+
+        # the reference hands the bare nn.LayerNorm (eps 1e-5) to the attention (attention.py:338, D5)
+        self.attn = MultiScaleAttention(
+            dim, num_heads=num_heads, qkv_bias=qkv_bias, drop_rate=drop_rate, kernel_q=kernel_q,
+            kernel_kv=kernel_kv, stride_q=stride_q, stride_kv=stride_kv, norm_layer=nn.LayerNorm,
+            has_cls_embed=has_cls_embed, mode=mode, use_query_residual_pool=use_query_residual_pool,
+            expand_channel=self.expand_channel, expand_to_dim=dim_out)
+        if self.expand_channel:
+            dim = dim_out
+            self.dim = dim_out
+
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        mlp_hidden_dim = int(dim * mlp_ratio)
+        self.has_cls_embed = has_cls_embed
+        mlp_dim_out = dim * up_rate if up_rate is not None and up_rate > 1 else dim_out
+        self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, out_features=mlp_dim_out,
+                       act_layer=act_layer, drop_rate=drop_rate)
+        if dim != dim_out:
+            self.proj = nn.Linear(dim, dim_out)
+        if self.expand_channel:
+            self.proj_max_pool = nn.Linear(dim_in, dim_out)
+        self.pool_skip = (nn.MaxPool3d(kernel_skip, stride_skip, padding_skip, ceil_mode=False)
+                          if len(kernel_skip) > 0 else None)
+        self.pool_skip_norm = None
+
+    def _skip_is_identity(self):
+        p = self.pool_skip
+        if p is None:
+            return True
+        k = [p.kernel_size] * 3 if isinstance(p.kernel_size, int) else list(p.kernel_size)
+        s = [p.stride] * 3 if isinstance(p.stride, int) else list(p.stride)
+        return all(v == 1 for v in k) and all(v == 1 for v in s)   # MaxPool3d([1,1,1]) == identity (D6)
+
+    def forward(self, x, thw_shape):
+        _no_grad_only(x)
+        dt = _compute_dtype(x)
+        x = x.to(dt).contiguous()
+        B = x.shape[0]
+        p_drop = getattr(self.drop_path, "drop_prob", 0.0) or 0.0
+        # one draw per drop_path call, in the reference's order (attention branch, then MLP branch)
+        s_attn = drop_path_scale(B, p_drop, self.training, x.device)
+        s_mlp = drop_path_scale(B, p_drop, self.training, x.device)
+
+        xn = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        if self.expand_channel and not self.pool_skip_use_conv:
+            x = ops.linear(x, cached_weight(self.proj_max_pool.weight, dt), self.proj_max_pool.bias)
+        if self._skip_is_identity():
+            x_res = x
+        else:
+            x_res, _ = attention_pool(x, self.pool_skip, thw_shape, has_cls_embed=self.has_cls_embed)
+        # x = x_res + drop_path(proj(attn))  — residual and DropPath scale live in the proj GEMM epilogue
+        x, thw_new = self.attn(xn, thw_shape, residual=x_res, row_scale=s_attn)
+        x_norm = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        if self.dim != self.dim_out:
+            x = ops.linear(x_norm, cached_weight(self.proj.weight, dt), self.proj.bias)
+        # out = x + drop_path(mlp(x_norm)) — residual and scale in the fc2 GEMM epilogue
+        out = self.mlp(x_norm, residual=x, row_scale=s_mlp)
+        return out, thw_new

@@ -1,0 +1,119 @@
+// Shared helpers for libmvit_b200 (sm_100a).  No torch / ATen types anywhere in this library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mvit_b200.h"
+
+namespace mvit {
+
+// thread-local error string behind mvit_last_error()
+void set_error(const char *fmt, ...);
+
+#define MVIT_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::mvit::set_error(__VA_ARGS__);  \
+      return -1;                       \
+    }                                  \
+  } while (0)
+
+#define MVIT_CUDA_OK(expr)                                                          \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::mvit::set_error("%s failed: %s", #expr, cudaGetErrorString(e__));           \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+
+#define MVIT_LAUNCH_OK(name)                                                        \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      ::mvit::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));  \
+      return -3;                                                                    \
+    }                                                                               \
+  } while (0)
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> struct DType;
+template <> struct DType<float> {
+  static constexpr int id = MVIT_F32;
+  static constexpr int vec = 4;  // elements per 16-byte vector
+};
+template <> struct DType<bf16> {
+  static constexpr int id = MVIT_BF16;
+  static constexpr int vec = 8;
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector <-> fp32 registers
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ __forceinline__ static void load(const float *p, float (&f)[4]) {
+    float4 v = *reinterpret_cast<const float4 *>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ __forceinline__ static void store(float *p, const float (&f)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  __device__ __forceinline__ static void load(const bf16 *p, float (&f)[8]) {
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ static void store(bf16 *p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace mvit

@@ -1,0 +1,19 @@
+#pragma once
+#include "common.cuh"
+
+namespace mvit {
+
+struct LinearArgs {
+  const void *x, *w, *residual;
+  const float *bias, *row_scale;
+  void *y;
+  int64_t M, rows_per_sample, ldy, ldr;
+  int N, K, epilogue;
+};
+
+int linear_simt(const LinearArgs &a, int dtype, cudaStream_t st);
+// tcgen05 path (gemm_tc.cu), bf16 only
+int linear_tc(const LinearArgs &a, cudaStream_t st);
+bool linear_tc_supported(const LinearArgs &a, const char **why);
+
+}  // namespace mvit

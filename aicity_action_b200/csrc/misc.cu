@@ -1,0 +1,102 @@
+// Small memory-bound kernels around the block stack: positional-embedding add and mean-pool + head.
+#include "common.cuh"
+
+namespace mvit {
+
+// x[b, t*HW + s, c] = src[...] + pos_spatial[s, c] + pos_temporal[t, c]
+// (video_model_builder.py:1206-1223: spatial.repeat(1,T,1) + repeat_interleave(temporal, HW))
+template <typename TS, typename TD>
+__global__ void pos_embed_add_kernel(const TS *__restrict__ src, const float *__restrict__ ps,
+                                     const float *__restrict__ pt, TD *__restrict__ dst, int64_t total,
+                                     int T, int HW, int C) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    const int64_t tok = (i / C) % ((int64_t)T * HW);
+    const int s = (int)(tok % HW), t = (int)(tok / HW);
+    dst[i] = from_f32<TD>(to_f32(src[i]) + (ps[(int64_t)s * C + c] + pt[(int64_t)t * C + c]));
+  }
+}
+
+// one CTA per sample: feat = mean over tokens, logits = feat·Wᵀ + b, optional softmax
+template <typename T>
+__global__ void __launch_bounds__(256) mean_head_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                        const float *__restrict__ bias,
+                                                        float *__restrict__ feat_out, float *__restrict__ out,
+                                                        int L, int C, int NCLS, int apply_softmax) {
+  extern __shared__ float sm[];  // feat[C] + logits[NCLS]
+  float *feat = sm, *logits = sm + C;
+  const int b = blockIdx.x;
+  const T *px = x + (int64_t)b * L * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += to_f32(px[(int64_t)l * C + c]);
+    feat[c] = s / (float)L;
+    if (feat_out) feat_out[(int64_t)b * C + c] = feat[c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < NCLS; n += blockDim.x >> 5) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(feat[c], w[(int64_t)n * C + c], s);
+    s = warp_sum(s);
+    if (lane == 0) logits[n] = s + (bias ? bias[n] : 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (apply_softmax) {
+      float m = -INFINITY;
+      for (int n = 0; n < NCLS; ++n) m = fmaxf(m, logits[n]);
+      float z = 0.f;
+      for (int n = 0; n < NCLS; ++n) z += expf(logits[n] - m);
+      for (int n = 0; n < NCLS; ++n) out[(int64_t)b * NCLS + n] = expf(logits[n] - m) / z;
+    } else {
+      for (int n = 0; n < NCLS; ++n) out[(int64_t)b * NCLS + n] = logits[n];
+    }
+  }
+}
+
+}  // namespace mvit
+
+extern "C" int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
+                                  const float *pos_temporal, void *dst, int B, int T, int HW, int C,
+                                  int dtype, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(src && dst && pos_spatial && pos_temporal, "pos_embed_add: null pointer");
+  MVIT_REQUIRE(B >= 0 && T > 0 && HW > 0 && C > 0, "pos_embed_add: bad shape");
+  if (B == 0) return 0;
+  const int64_t total = (int64_t)B * T * HW * C;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + threads - 1) / threads, (int64_t)num_sms() * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define PE(TS, TD)                                                                                     \
+  pos_embed_add_kernel<TS, TD><<<blocks, threads, 0, st>>>(static_cast<const TS *>(src), pos_spatial,  \
+                                                           pos_temporal, static_cast<TD *>(dst), total, T, HW, C)
+  if (src_dtype == MVIT_F32 && dtype == MVIT_F32) PE(float, float);
+  else if (src_dtype == MVIT_F32 && dtype == MVIT_BF16) PE(float, bf16);
+  else if (src_dtype == MVIT_BF16 && dtype == MVIT_BF16) PE(bf16, bf16);
+  else if (src_dtype == MVIT_BF16 && dtype == MVIT_F32) PE(bf16, float);
+  else MVIT_REQUIRE(false, "pos_embed_add: unknown dtype");
+#undef PE
+  MVIT_LAUNCH_OK("pos_embed_add");
+  return 0;
+}
+
+extern "C" int mvit_mean_head_fwd(const void *x, const float *w, const float *bias, float *feat_out,
+                                  float *out, int B, int L, int C, int num_classes, int apply_softmax,
+                                  int dtype, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(x && w && out, "mean_head: null pointer");
+  MVIT_REQUIRE(B >= 0 && L > 0 && C > 0 && num_classes > 0, "mean_head: bad shape");
+  if (B == 0) return 0;
+  const size_t smem = (size_t)(C + num_classes) * sizeof(float);
+  MVIT_REQUIRE(smem <= 48 * 1024, "mean_head: C + classes too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MVIT_F32)
+    mean_head_kernel<float><<<B, 256, smem, st>>>(static_cast<const float *>(x), w, bias, feat_out, out, L, C, num_classes, apply_softmax);
+  else if (dtype == MVIT_BF16)
+    mean_head_kernel<bf16><<<B, 256, smem, st>>>(static_cast<const bf16 *>(x), w, bias, feat_out, out, L, C, num_classes, apply_softmax);
+  else MVIT_REQUIRE(false, "mean_head: unknown dtype");
+  MVIT_LAUNCH_OK("mean_head");
+  return 0;
+}

@@ -1,0 +1,177 @@
+// attention_pool (attention.py:12-83): depthwise Conv3d / MaxPool3d / AvgPool3d over the (T,H,W) token
+// grid, fused with the LayerNorm that follows it (attention.py:66-67), operating on channels-last
+// tokens in place of the reference's [B*h, d, T, H, W] round trip (attention.py:34-36, 58-60).
+//
+// Generic kernel (any kernel size / stride / d % 32 == 0, cls token, three modes): one warp per output
+// token*head, lane owns channels {lane, lane+32, ...} so every global access of a warp is one contiguous
+// d*sizeof(T) segment.  The tuned stride-(1,s,s) 3x3x3 path lives in pool_tiled.cu.
+#include "common.cuh"
+
+namespace mvit {
+
+struct PoolParams {
+  int64_t in_bs, in_ls, in_hs, out_bs, out_ls, out_hs;
+  int B, heads, d, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo;
+  int has_cls, has_ln;
+  float eps;
+};
+
+template <typename T, int NC, int MODE>
+__global__ void __launch_bounds__(256) pool_generic_kernel(const T *__restrict__ in,
+                                                           const float *__restrict__ weight,
+                                                           const float *__restrict__ gamma,
+                                                           const float *__restrict__ beta,
+                                                           T *__restrict__ out, PoolParams p) {
+  extern __shared__ float w_s[];  // [taps][d] (CONV only)
+  const int taps = p.kt * p.kh * p.kw;
+  if (MODE == MVIT_POOL_CONV) {
+    for (int i = threadIdx.x; i < taps * p.d; i += blockDim.x) {
+      const int tap = i / p.d, c = i - tap * p.d;
+      w_s[i] = weight[c * taps + tap];
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int Lo = p.To * p.Ho * p.Wo + p.has_cls;
+  const int64_t total = (int64_t)p.B * Lo * p.heads;
+  const int64_t o = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= total) return;
+  const int head = (int)(o % p.heads);
+  const int64_t bl = o / p.heads;
+  const int lo = (int)(bl % Lo);
+  const int b = (int)(bl / Lo);
+  const T *src = in + b * p.in_bs + head * p.in_hs;
+  float acc[NC];
+  if (p.has_cls && lo == 0) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = to_f32(src[lane + 32 * j]);
+  } else {
+    const int l = lo - p.has_cls;
+    const int wo = l % p.Wo, ho = (l / p.Wo) % p.Ho, to = l / (p.Wo * p.Ho);
+    const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = (MODE == MVIT_POOL_MAX) ? -INFINITY : 0.f;
+    for (int a = 0; a < p.kt; ++a) {
+      const int t = t0 + a;
+      if (t < 0 || t >= p.T) continue;
+      for (int bq = 0; bq < p.kh; ++bq) {
+        const int h = h0 + bq;
+        if (h < 0 || h >= p.H) continue;
+        for (int c = 0; c < p.kw; ++c) {
+          const int w = w0 + c;
+          if (w < 0 || w >= p.W) continue;
+          const T *px = src + ((int64_t)((t * p.H + h) * p.W + w) + p.has_cls) * p.in_ls;
+          const float *pw = w_s + ((a * p.kh + bq) * p.kw + c) * p.d;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            const float v = to_f32(px[lane + 32 * j]);
+            if (MODE == MVIT_POOL_CONV) acc[j] = fmaf(v, pw[lane + 32 * j], acc[j]);
+            else if (MODE == MVIT_POOL_MAX) acc[j] = fmaxf(acc[j], v);
+            else acc[j] += v;
+          }
+        }
+      }
+    }
+    if (MODE == MVIT_POOL_AVG) {
+      const float inv = 1.0f / (float)taps;  // count_include_pad=True (torch default)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[j] *= inv;
+    }
+  }
+  if (p.has_ln) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s += acc[j];
+    const float mean = warp_sum(s) / (float)p.d;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float dlt = acc[j] - mean;
+      ss += dlt * dlt;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)p.d + p.eps);
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      acc[j] = (acc[j] - mean) * rstd * gamma[lane + 32 * j] + beta[lane + 32 * j];
+  }
+  T *dst = out + b * p.out_bs + (int64_t)lo * p.out_ls + head * p.out_hs;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) dst[lane + 32 * j] = from_f32<T>(acc[j]);
+}
+
+template <typename T, int NC>
+static int launch_generic(const void *in, const float *w, const float *g, const float *b, void *out,
+                          const PoolParams &p, int mode, cudaStream_t st) {
+  const int Lo = p.To * p.Ho * p.Wo + p.has_cls;
+  const int64_t total = (int64_t)p.B * Lo * p.heads;
+  const int threads = 256;
+  const int64_t blocks = (total + 7) / 8;
+  MVIT_REQUIRE(blocks < ((int64_t)1 << 31), "attention_pool: grid too large");
+  const size_t smem = mode == MVIT_POOL_CONV ? (size_t)p.kt * p.kh * p.kw * p.d * sizeof(float) : 0;
+  MVIT_REQUIRE(smem <= 48 * 1024, "attention_pool: conv kernel too large for the generic path");
+  const T *pi = static_cast<const T *>(in);
+  T *po = static_cast<T *>(out);
+  if (mode == MVIT_POOL_CONV)
+    pool_generic_kernel<T, NC, MVIT_POOL_CONV><<<(unsigned)blocks, threads, smem, st>>>(pi, w, g, b, po, p);
+  else if (mode == MVIT_POOL_MAX)
+    pool_generic_kernel<T, NC, MVIT_POOL_MAX><<<(unsigned)blocks, threads, 0, st>>>(pi, w, g, b, po, p);
+  else
+    pool_generic_kernel<T, NC, MVIT_POOL_AVG><<<(unsigned)blocks, threads, 0, st>>>(pi, w, g, b, po, p);
+  MVIT_LAUNCH_OK("attention_pool(generic)");
+  return 0;
+}
+
+template <typename T>
+static int dispatch_generic(const void *in, const float *w, const float *g, const float *b, void *out,
+                            const PoolParams &p, int mode, cudaStream_t st) {
+  switch (p.d / 32) {
+    case 1: return launch_generic<T, 1>(in, w, g, b, out, p, mode, st);
+    case 2: return launch_generic<T, 2>(in, w, g, b, out, p, mode, st);
+    case 3: return launch_generic<T, 3>(in, w, g, b, out, p, mode, st);
+    case 4: return launch_generic<T, 4>(in, w, g, b, out, p, mode, st);
+  }
+  MVIT_REQUIRE(false, "attention_pool: head_dim %d unsupported (need 32..128, multiple of 32)", p.d);
+}
+
+// tuned path (pool_tiled.cu); returns 1 if it does not apply
+int pool_tiled_try(const void *in, const float *w, const float *g, const float *b, void *out,
+                   const PoolParams &p, int mode, int dtype, cudaStream_t st);
+
+}  // namespace mvit
+
+extern "C" int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
+                                       const float *weight, const float *gamma, const float *beta,
+                                       void *out, int64_t out_bs, int64_t out_ls, int64_t out_hs, int B,
+                                       int heads, int d, int T, int H, int W, int kt, int kh, int kw,
+                                       int st, int sh, int sw, int mode, int has_cls, float eps,
+                                       int dtype, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(in && out, "attention_pool: null pointer");
+  MVIT_REQUIRE(B >= 0 && heads > 0 && d > 0 && T > 0 && H > 0 && W > 0, "attention_pool: bad shape");
+  MVIT_REQUIRE(kt > 0 && kh > 0 && kw > 0 && st > 0 && sh > 0 && sw > 0, "attention_pool: bad kernel/stride");
+  MVIT_REQUIRE(mode == MVIT_POOL_CONV || mode == MVIT_POOL_MAX || mode == MVIT_POOL_AVG,
+               "attention_pool: unknown mode %d", mode);
+  MVIT_REQUIRE(mode != MVIT_POOL_CONV || weight, "attention_pool: conv mode needs a weight");
+  MVIT_REQUIRE((gamma == nullptr) == (beta == nullptr), "attention_pool: gamma/beta must both be set or NULL");
+  MVIT_REQUIRE(d % 32 == 0 && d <= 128, "attention_pool: head_dim %d unsupported (multiple of 32, <= 128)", d);
+  MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "attention_pool: unknown dtype %d", dtype);
+  if (B == 0) return 0;
+  PoolParams p;
+  p.in_bs = in_bs; p.in_ls = in_ls; p.in_hs = in_hs;
+  p.out_bs = out_bs; p.out_ls = out_ls; p.out_hs = out_hs;
+  p.B = B; p.heads = heads; p.d = d; p.T = T; p.H = H; p.W = W;
+  p.kt = kt; p.kh = kh; p.kw = kw; p.st = st; p.sh = sh; p.sw = sw;
+  p.pt = kt / 2; p.ph = kh / 2; p.pw = kw / 2;
+  p.To = (T + 2 * p.pt - kt) / st + 1;
+  p.Ho = (H + 2 * p.ph - kh) / sh + 1;
+  p.Wo = (W + 2 * p.pw - kw) / sw + 1;
+  MVIT_REQUIRE(p.To > 0 && p.Ho > 0 && p.Wo > 0, "attention_pool: empty output");
+  p.has_cls = has_cls ? 1 : 0;
+  p.has_ln = gamma ? 1 : 0;
+  p.eps = eps;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int r = pool_tiled_try(in, weight, gamma, beta, out, p, mode, dtype, s);
+  if (r <= 0) return r;
+  if (dtype == MVIT_F32) return dispatch_generic<float>(in, weight, gamma, beta, out, p, mode, s);
+  return dispatch_generic<bf16>(in, weight, gamma, beta, out, p, mode, s);
+}

@@ -1,0 +1,295 @@
+"""Drop-in for the `MViT` model of slowfast/models/video_model_builder.py:794-1335 (plus PatchEmbed,
+stem_helper.py:308-338; TransformerBasicHead, head_helper.py:369-417; round_width, models/utils.py:8-22).
+
+Same cfg keys (MVIT.*, MODEL.*, DATA.*), same parameter names / shapes / registration order (so
+`state_dict()` round-trips with reference checkpoints and a seeded construction draws the same
+random numbers), same `forward(x: list[Tensor], ...)` contract.  The 16/24 blocks, the LayerNorms,
+the positional-embedding add and the pooled head run in libmvit_b200.so; see attention.py.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+from torch.nn.init import trunc_normal_
+
+from . import ops
+from .attention import MultiScaleBlock, _compute_dtype, _no_grad_only
+from .weights import cached_weight
+
+
+def round_width(width, multiplier, min_width=1, divisor=1, verbose=False):
+    """models/utils.py:8-22."""
+    if not multiplier:
+        return width
+    width *= multiplier
+    min_width = min_width or divisor
+    width_out = max(min_width, int(width + divisor / 2) // divisor * divisor)
+    if width_out < 0.9 * width:
+        width_out += divisor
+    return int(width_out)
+
+
+class PatchEmbed(nn.Module):
+    """Conv3d(3->96, k(3,7,7), s(2,4,4), p(1,3,3)) -> tokens [B, T'H'W', C] (stem_helper.py:308-338).
+
+    The convolution is evaluated channels-last (NDHWC) so its output *is* the token tensor — the
+    `flatten(2).transpose(1,2)` of the reference costs nothing."""
+
+    def __init__(self, dim_in=3, dim_out=768, kernel=(1, 16, 16), stride=(1, 4, 4), padding=(1, 7, 7),
+                 conv_2d=False):
+        super().__init__()
+        conv = nn.Conv2d if conv_2d else nn.Conv3d
+        self.proj = conv(dim_in, dim_out, kernel_size=kernel, stride=stride, padding=padding)
+        self.conv_2d = conv_2d
+
+    def forward(self, x, dtype=None):
+        if not x.is_cuda:
+            raise ops._lib.MvitLibraryError("aicity_action_b200 runs on CUDA tensors only (no CPU fallback)")
+        dtype = dtype or x.dtype
+        w = cached_weight(self.proj.weight, dtype)
+        b = cached_weight(self.proj.bias, dtype)
+        if self.conv_2d:
+            y = torch.nn.functional.conv2d(x.to(dtype).contiguous(memory_format=torch.channels_last), w, b,
+                                           self.proj.stride, self.proj.padding)
+            return y.permute(0, 2, 3, 1).flatten(1, 2)
+        y = torch.nn.functional.conv3d(x.to(dtype).contiguous(memory_format=torch.channels_last_3d),
+                                       w.contiguous(memory_format=torch.channels_last_3d), b,
+                                       self.proj.stride, self.proj.padding)
+        return y.permute(0, 2, 3, 4, 1).flatten(1, 3)      # [B, T'H'W', C]; a view when y is NDHWC
+
+
+class TransformerBasicHead(nn.Module):
+    """Dropout -> Linear -> (Softmax | Sigmoid when not training)  (head_helper.py:369-417)."""
+
+    def __init__(self, dim_in, num_classes, dropout_rate=0.0, act_func="softmax", use_act_in_train=False):
+        super().__init__()
+        if dropout_rate > 0.0:
+            self.dropout = nn.Dropout(dropout_rate)
+        self.projection = nn.Linear(dim_in, num_classes, bias=True)
+        self.use_act_in_train = use_act_in_train
+        if act_func == "softmax":
+            self.act = nn.Softmax(dim=1)
+        elif act_func == "sigmoid":
+            self.act = nn.Sigmoid()
+        else:
+            raise NotImplementedError(f"{act_func} is not supported as an activation function.")
+
+    def forward_tokens(self, x):
+        """x: [B, L, C] tokens; fused mean over L -> projection -> activation, fp32 result."""
+        act = self.use_act_in_train or not self.training
+        drop = hasattr(self, "dropout") and self.training and self.dropout.p > 0
+        softmax = act and isinstance(self.act, nn.Softmax)
+        if not drop:
+            out = ops.mean_head(x, self.projection.weight, self.projection.bias, softmax=softmax)
+        else:
+            _, feat = ops.mean_head(x, self.projection.weight, self.projection.bias, softmax=False, want_feat=True)
+            feat = self.dropout(feat)
+            out = ops.mean_head(feat.unsqueeze(1), self.projection.weight, self.projection.bias, softmax=softmax)
+        if act and not softmax:
+            out = self.act(out)
+        return out
+
+    def forward(self, x):
+        return self.forward_tokens(x.unsqueeze(1) if x.ndim == 2 else x)
+
+
+class MViT(nn.Module):
+    """video_model_builder.py:794-1335 (classification path; RoI / multi-dataset / contrastive heads are
+    out of scope and rejected at construction)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        assert cfg.DATA.TRAIN_CROP_SIZE == cfg.DATA.TEST_CROP_SIZE
+        self.cfg = cfg
+        if cfg.DETECTION.ENABLE or cfg.MODEL.USE_MULTI_HEAD or cfg.CONTRA.ENABLE \
+                or cfg.DETECTION.USE_SPATIAL_MAXPOOL_BEFORE_PROJ:
+            raise NotImplementedError("aicity_action_b200.MViT implements the TransformerBasicHead path only")
+        self.use_query_residual_pool = cfg.MVIT.Q_POOL_RESIDUAL
+        self.q_pool_all = cfg.MVIT.Q_POOL_ALL
+        self.channel_expand_front = cfg.MVIT.CHANNEL_EXPAND_FRONT
+        self.pool_skip_use_conv = cfg.MVIT.POOL_SKIP_USE_CONV
+        self.direct_input = cfg.MVIT.DIRECT_INPUT
+        pool_first = cfg.MVIT.POOL_FIRST
+
+        spatial_size = cfg.DATA.TRAIN_CROP_SIZE
+        temporal_size = cfg.DATA.NUM_FRAMES
+        in_chans = cfg.DATA.INPUT_CHANNEL_NUM[0]
+        use_2d_patch = cfg.MVIT.PATCH_2D
+        self.patch_stride = list(cfg.MVIT.PATCH_STRIDE)
+        if use_2d_patch:
+            self.patch_stride = [1] + self.patch_stride
+        num_classes = cfg.MODEL.NUM_CLASSES
+        embed_dim = cfg.MVIT.EMBED_DIM
+        dim_out = embed_dim
+        num_heads = cfg.MVIT.NUM_HEADS
+        mlp_ratio = cfg.MVIT.MLP_RATIO
+        qkv_bias = cfg.MVIT.QKV_BIAS
+        self.drop_rate = cfg.MVIT.DROPOUT_RATE
+        depth = cfg.MVIT.DEPTH
+        drop_path_rate = cfg.MVIT.DROPPATH_RATE
+        mode = cfg.MVIT.MODE
+        self.cls_embed_on = cfg.MVIT.CLS_EMBED_ON
+        self.sep_pos_embed = cfg.MVIT.SEP_POS_EMBED
+        if cfg.MVIT.NORM != "layernorm":
+            raise NotImplementedError("Only supports layernorm.")
+        norm_layer = partial(nn.LayerNorm, eps=1e-6)
+        self.num_classes = num_classes
+
+        self.patch_embed = PatchEmbed(dim_in=in_chans, dim_out=embed_dim, kernel=cfg.MVIT.PATCH_KERNEL,
+                                      stride=cfg.MVIT.PATCH_STRIDE, padding=cfg.MVIT.PATCH_PADDING,
+                                      conv_2d=use_2d_patch)
+        self.input_dims = [temporal_size, spatial_size, spatial_size]
+        self.patch_dims = [self.input_dims[i] // self.patch_stride[i] for i in range(3)]
+        num_patches = math.prod(self.patch_dims)
+
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+
+        if self.cls_embed_on:
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+            pos_embed_dim = num_patches + 1
+        else:
+            pos_embed_dim = num_patches
+        if self.sep_pos_embed:
+            self.pos_embed_spatial = nn.Parameter(torch.zeros(1, self.patch_dims[1] * self.patch_dims[2], embed_dim))
+            self.pos_embed_temporal = nn.Parameter(torch.zeros(1, self.patch_dims[0], embed_dim))
+            if self.cls_embed_on:
+                self.pos_embed_class = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        else:
+            self.pos_embed = nn.Parameter(torch.zeros(1, pos_embed_dim, embed_dim))
+        if self.drop_rate > 0.0:
+            self.pos_drop = nn.Dropout(p=self.drop_rate)
+
+        # ---- per-block pooling schedule (video_model_builder.py:921-980) ----
+        dim_mul, head_mul = [1.0] * (depth + 1), [1.0] * (depth + 1)
+        for i, m in cfg.MVIT.DIM_MUL:
+            dim_mul[i] = m
+        for i, m in cfg.MVIT.HEAD_MUL:
+            head_mul[i] = m
+        pool_q = [[] for _ in range(depth)]
+        pool_kv = [[] for _ in range(depth)]
+        stride_q = [[] for _ in range(depth)]
+        stride_kv = [[] for _ in range(depth)]
+        kvq = cfg.MVIT.POOL_KVQ_KERNEL
+        for ent in cfg.MVIT.POOL_Q_STRIDE:
+            stride_q[ent[0]] = list(ent[1:])
+            pool_q[ent[0]] = list(kvq) if kvq is not None else [s + 1 if s > 1 else s for s in ent[1:]]
+        if self.q_pool_all:
+            for i in range(depth):
+                if not pool_q[i]:
+                    pool_q[i] = list(kvq)
+                    stride_q[i] = [1, 1, 1]
+        if cfg.MVIT.POOL_KV_STRIDE_ADAPTIVE is not None:
+            # the reference also writes the derived list back into cfg (video_model_builder.py:958-967)
+            _stride_kv = list(cfg.MVIT.POOL_KV_STRIDE_ADAPTIVE)
+            cfg.MVIT.POOL_KV_STRIDE = []
+            for i in range(depth):
+                if len(stride_q[i]) > 0:
+                    _stride_kv = [max(_stride_kv[d] // stride_q[i][d], 1) for d in range(len(_stride_kv))]
+                cfg.MVIT.POOL_KV_STRIDE.append([i] + _stride_kv)
+        for ent in (cfg.MVIT.POOL_KV_STRIDE or []):
+            stride_kv[ent[0]] = list(ent[1:])
+            pool_kv[ent[0]] = list(kvq) if kvq is not None else [s + 1 if s > 1 else s for s in ent[1:]]
+
+        self.norm_stem = norm_layer(embed_dim) if cfg.MVIT.NORM_STEM else None
+        self.act_checkpoint = bool(cfg.MODEL.ACT_CHECKPOINT)
+
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            num_heads = round_width(num_heads, head_mul[i])
+            if self.channel_expand_front:
+                embed_dim = round_width(embed_dim, 1.0 if i == 0 else dim_mul[i - 1], divisor=num_heads)
+                dim_out = round_width(dim_out, dim_mul[i], divisor=num_heads)
+            else:
+                embed_dim = round_width(embed_dim, dim_mul[i], divisor=num_heads)
+                dim_out = round_width(embed_dim, dim_mul[i + 1], divisor=round_width(num_heads, head_mul[i + 1]))
+            self.blocks.append(MultiScaleBlock(
+                dim=embed_dim, dim_out=dim_out, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                drop_rate=self.drop_rate, drop_path=dpr[i], norm_layer=norm_layer, kernel_q=pool_q[i],
+                kernel_kv=pool_kv[i], stride_q=stride_q[i], stride_kv=stride_kv[i], mode=mode,
+                has_cls_embed=self.cls_embed_on, pool_first=pool_first,
+                use_query_residual_pool=self.use_query_residual_pool,
+                channel_expand_front=self.channel_expand_front, pool_skip_use_conv=self.pool_skip_use_conv))
+        embed_dim = dim_out
+        self.norm = norm_layer(embed_dim) if not cfg.MVIT.NO_NORM_BEFORE_AVG else None
+
+        if self.sep_pos_embed:
+            trunc_normal_(self.pos_embed_spatial, std=0.02)
+            trunc_normal_(self.pos_embed_temporal, std=0.02)
+            if self.cls_embed_on:
+                trunc_normal_(self.pos_embed_class, std=0.02)
+        else:
+            trunc_normal_(self.pos_embed, std=0.02)
+        if self.cls_embed_on:
+            trunc_normal_(self.cls_token, std=0.02)
+
+        self.head = TransformerBasicHead(embed_dim, num_classes, dropout_rate=cfg.MODEL.DROPOUT_RATE,
+                                         act_func=cfg.MODEL.HEAD_ACT,
+                                         use_act_in_train=cfg.MODEL.USE_HEAD_ACT_IN_TRAIN)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        if self.cfg.MVIT.ZERO_DECAY_POS_CLS:
+            if self.sep_pos_embed:
+                names = {"pos_embed_spatial", "pos_embed_temporal", "pos_embed_class"}
+                return names | {"cls_token"} if self.cls_embed_on else names
+            return {"pos_embed", "cls_token"} if self.cls_embed_on else {"pos_embed"}
+        return {}
+
+    # ------------------------------------------------------------------------------------
+    def _pos_table(self, dtype):
+        """Full [1+N or N, C] fp32 table for the generic (cls / non-separable) path."""
+        if self.sep_pos_embed:
+            T, H, W = self.patch_dims
+            pos = self.pos_embed_spatial.repeat(1, T, 1) + torch.repeat_interleave(
+                self.pos_embed_temporal, H * W, dim=1)
+            if self.cls_embed_on:
+                pos = torch.cat([self.pos_embed_class, pos], 1)
+            return pos
+        return self.pos_embed
+
+    def forward_features(self, x, dtype):
+        tokens = self.patch_embed(x, dtype)                      # [B, N, C]
+        T, H, W = self.patch_dims
+        B = tokens.shape[0]
+        if self.sep_pos_embed and not self.cls_embed_on:
+            x = ops.pos_embed_add(tokens, self.pos_embed_spatial, self.pos_embed_temporal, T, dtype)
+        else:
+            if self.cls_embed_on:
+                tokens = torch.cat((self.cls_token.to(tokens.dtype).expand(B, -1, -1), tokens), dim=1)
+            pos = self._pos_table(dtype).detach()
+            zero_t = torch.zeros((1, tokens.shape[-1]), dtype=torch.float32, device=tokens.device)
+            x = ops.pos_embed_add(tokens, pos, zero_t, 1, dtype)
+        if self.drop_rate and self.training:
+            x = self.pos_drop(x)
+        if self.norm_stem is not None:
+            x = ops.layernorm(x, self.norm_stem.weight, self.norm_stem.bias, self.norm_stem.eps)
+        thw = [T, H, W]
+        for blk in self.blocks:
+            x, thw = blk(x, thw)
+        if self.norm is not None:
+            x = ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        return x, thw
+
+    def forward(self, x, bboxes=None, dataset_name=None, run_cross_proj=False, use_moco=False,
+                moco_momentum=0.9):
+        if not self.direct_input:
+            x = x[0]
+        _no_grad_only(x)
+        dtype = _compute_dtype(x)
+        x, _ = self.forward_features(x, dtype)
+        if self.cls_embed_on:
+            x = x[:, :1]
+        return self.head.forward_tokens(x)

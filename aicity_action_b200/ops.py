@@ -1,0 +1,208 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mvit_b200.h).
+
+PyTorch is used here only for device memory (`torch.empty`) and the current CUDA stream; every
+computation below is one call into libmvit_b200.so.  Tensors must live on a CUDA device: there
+is no CPU implementation in the product (the CPU oracle lives in oracle/ and is test-only).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (BF16, EPI_GELU, EPI_NONE, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, POOL_AVG,
+                   POOL_CONV, POOL_MAX, check)
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+POOL_MODES = {"conv": POOL_CONV, "max": POOL_MAX, "avg": POOL_AVG}
+
+# number of C-ABI kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}: the B200 path computes in float32 or bfloat16") from None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MvitLibraryError(
+                "aicity_action_b200 kernels run on CUDA tensors only (no CPU fallback); got a CPU tensor")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.detach().float().contiguous()
+    return t
+
+
+def pooled_thw(thw: Sequence[int], kernel: Sequence[int], stride: Sequence[int]):
+    """Output grid of Conv3d/MaxPool3d with padding k//2 and ceil_mode=False."""
+    return [(n + 2 * (k // 2) - k) // s + 1 for n, k, s in zip(thw, kernel, stride)]
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    _need_cuda(x, gamma, beta)
+    x = x.contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x) if out is None else out
+    gamma, beta = _f32c(gamma), _f32c(beta)
+    check(_lib.load().mvit_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, C, float(eps),
+                                         _dt(x), _stream()), "mvit_layernorm_fwd")
+    launch_count += 1
+    return y
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+           gelu: bool = False, out: Optional[torch.Tensor] = None, impl: int = IMPL_AUTO) -> torch.Tensor:
+    """y = epi(x·wᵀ + bias)·row_scale + residual ; x [..., K], w [N, K] (same dtype as x)."""
+    global launch_count
+    _need_cuda(x, w, bias, residual, row_scale)
+    x = x.contiguous()
+    K = x.shape[-1]
+    N = w.shape[0]
+    assert w.shape[1] == K and w.dtype == x.dtype and w.is_contiguous(), "weight must be [N,K], contiguous, x.dtype"
+    M = x.numel() // K
+    y = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device) if out is None else out
+    assert y.is_contiguous() and y.numel() == M * N
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.numel() == M * N and residual.dtype == x.dtype
+    rows_per_sample = 0
+    if row_scale is not None:
+        row_scale = _f32c(row_scale).reshape(-1)
+        assert M % row_scale.numel() == 0
+        rows_per_sample = M // row_scale.numel()
+    bias = _f32c(bias)
+    check(_lib.load().mvit_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(row_scale),
+                                      rows_per_sample, _ptr(y), M, N, K, N, N,
+                                      EPI_GELU if gelu else EPI_NONE, _dt(x), impl, _stream()),
+          "mvit_linear_fwd")
+    launch_count += 1
+    return y
+
+
+def attention_pool_strided(src: torch.Tensor, src_offset: int, in_strides: Tuple[int, int, int], B: int,
+                           heads: int, d: int, thw: Sequence[int], kernel: Sequence[int],
+                           stride: Sequence[int], mode: str, weight: Optional[torch.Tensor],
+                           gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float,
+                           has_cls: bool, out: torch.Tensor, out_strides: Tuple[int, int, int]):
+    """Raw form: reads in[b,l,head,:] at src_offset + b*bs + l*ls + head*hs (element strides)."""
+    global launch_count
+    _need_cuda(src, out, weight, gamma, beta)
+    T, H, W = thw
+    weight, gamma, beta = _f32c(weight), _f32c(gamma), _f32c(beta)
+    if weight is not None:
+        weight = weight.reshape(d, -1)
+    base = src.data_ptr() + src_offset * src.element_size()
+    check(_lib.load().mvit_attention_pool_fwd(
+        base, in_strides[0], in_strides[1], in_strides[2], _ptr(weight), _ptr(gamma), _ptr(beta),
+        _ptr(out), out_strides[0], out_strides[1], out_strides[2], B, heads, d, T, H, W,
+        kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2], POOL_MODES[mode],
+        1 if has_cls else 0, float(eps), _dt(src), _stream()), "mvit_attention_pool_fwd")
+    launch_count += 1
+
+
+def attention_pool_heads(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[int], stride: Sequence[int], *,
+                         mode: str = "conv", weight: Optional[torch.Tensor] = None,
+                         ln: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
+                         has_cls: bool = False):
+    """x: any strided view [B, heads, L, d] with unit channel stride -> contiguous [B, heads, L', d]."""
+    B, heads, L, d = x.shape
+    assert x.stride(3) == 1
+    out_thw = pooled_thw(thw, kernel, stride)
+    Lo = out_thw[0] * out_thw[1] * out_thw[2] + (1 if has_cls else 0)
+    out = torch.empty((B, heads, Lo, d), dtype=x.dtype, device=x.device)
+    g, b, eps = ln if ln is not None else (None, None, 0.0)
+    attention_pool_strided(x, 0, (x.stride(0), x.stride(2), x.stride(1)), B, heads, d, thw, kernel, stride,
+                           mode, weight, g, b, eps, has_cls, out, (heads * Lo * d, d, Lo * d))
+    # note: `x` may be a view with a storage offset; data_ptr() already includes it
+    return out, out_thw
+
+
+def attention_pool_tokens(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[int], stride: Sequence[int], *,
+                          mode: str = "max", has_cls: bool = False, d: int = 96):
+    """x: [B, L, C] channels-last tokens -> [B, L', C] (skip-path pooling, attention.py:427-432)."""
+    x = x.contiguous()
+    B, L, Cc = x.shape
+    if Cc % d != 0:
+        d = 32 if Cc % 32 == 0 else None
+        if d is None:
+            raise _lib.MvitLibraryError(f"skip pooling needs channels % 32 == 0, got {Cc}")
+    heads = Cc // d
+    out_thw = pooled_thw(thw, kernel, stride)
+    Lo = out_thw[0] * out_thw[1] * out_thw[2] + (1 if has_cls else 0)
+    out = torch.empty((B, Lo, Cc), dtype=x.dtype, device=x.device)
+    attention_pool_strided(x, 0, (L * Cc, Cc, d), B, heads, d, thw, kernel, stride, mode, None, None, None,
+                           0.0, has_cls, out, (Lo * Cc, Cc, d))
+    return out, out_thw
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, add_q: bool, *,
+              want_lse: bool = False, impl: int = IMPL_AUTO):
+    """q [B,h,Lq,96], k/v [B,h,Lk,96] contiguous -> out [B, Lq, h*96] (+ lse [B,h,Lq] fp32)."""
+    global launch_count
+    _need_cuda(q, k, v)
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    B, h, Lq, d = q.shape
+    Lk = k.shape[2]
+    assert k.shape == (B, h, Lk, d) and v.shape == (B, h, Lk, d) and q.dtype == k.dtype == v.dtype
+    out = torch.empty((B, Lq, h * d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, h, Lq), dtype=torch.float32, device=q.device) if want_lse else None
+    check(_lib.load().mvit_attention_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, h, Lq, Lk, d,
+                                         float(scale), 1 if add_q else 0, _dt(q), impl, _stream()),
+          "mvit_attention_fwd")
+    launch_count += 1
+    return (out, lse) if want_lse else out
+
+
+def pos_embed_add(tokens: torch.Tensor, pos_spatial: torch.Tensor, pos_temporal: torch.Tensor, T: int,
+                  out_dtype: torch.dtype) -> torch.Tensor:
+    """tokens [B, T*HW, C] (fp32/bf16, contiguous) + separable pos-embed -> [B, T*HW, C] in out_dtype."""
+    global launch_count
+    _need_cuda(tokens, pos_spatial, pos_temporal)
+    tokens = tokens.contiguous()
+    B, N, Cc = tokens.shape
+    HW = N // T
+    out = torch.empty((B, N, Cc), dtype=out_dtype, device=tokens.device)
+    ps, pt = _f32c(pos_spatial).reshape(HW, Cc), _f32c(pos_temporal).reshape(T, Cc)
+    check(_lib.load().mvit_pos_embed_add(_ptr(tokens), _dt(tokens), _ptr(ps), _ptr(pt), _ptr(out), B, T, HW,
+                                         Cc, _DT[out_dtype], _stream()), "mvit_pos_embed_add")
+    launch_count += 1
+    return out
+
+
+def mean_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], softmax: bool,
+              want_feat: bool = False):
+    """x [B, L, C] -> fp32 [B, classes] (token mean -> Linear -> optional softmax)."""
+    global launch_count
+    _need_cuda(x, w, bias)
+    x = x.contiguous()
+    B, L, Cc = x.shape
+    w, bias = _f32c(w), _f32c(bias)
+    n = w.shape[0]
+    out = torch.empty((B, n), dtype=torch.float32, device=x.device)
+    feat = torch.empty((B, Cc), dtype=torch.float32, device=x.device) if want_feat else None
+    check(_lib.load().mvit_mean_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(feat), _ptr(out), B, L, Cc, n,
+                                         1 if softmax else 0, _dt(x), _stream()), "mvit_mean_head_fwd")
+    launch_count += 1
+    return (out, feat) if want_feat else out

@@ -1,0 +1,128 @@
+/*
+ * mvit_b200.h — C ABI of libmvit_b200.so: sm_100a kernels for the MViTv2 multiscale-attention path.
+ *
+ * The reference (JunweiLiang/aicity_action, a PySlowFast fork) has no native layer: its plug
+ * point is the Python module API of slowfast/models/attention.py.  This ABI is what the Python
+ * drop-in (aicity_action_b200/attention.py, mvit.py) binds with ctypes; each entry point names the
+ * reference code it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory,
+ *    the library never allocates or frees device memory and keeps no mutable global state;
+ *  - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and safe
+ *    under CUDA-graph capture (no synchronisation, no allocation);
+ *  - return value 0 = launched, negative = rejected before launch (bad shape / unsupported
+ *    combination / CUDA error); mvit_last_error() returns a thread-local message.  There is no CPU
+ *    fallback and no silent fallback of any kind: an unsupported request is an error;
+ *  - `dtype` selects the activation type: MVIT_F32 (fp32 storage, fp32 FMA arithmetic) or MVIT_BF16
+ *    (bf16 storage, fp32 accumulation; GEMM/attention run on tcgen05 tensor cores);
+ *  - LayerNorm gamma/beta, biases and depthwise-conv weights are always fp32; Linear weights have
+ *    the activation dtype;
+ *  - token tensors are channels-last: [B, L, C] with L = T*H*W (+1 leading cls token if has_cls).
+ */
+#ifndef MVIT_B200_H_
+#define MVIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVIT_F32 0
+#define MVIT_BF16 1
+
+/* pooling modes of attention_pool (attention.py:136-212) */
+#define MVIT_POOL_CONV 0 /* depthwise Conv3d, zero padding, no bias */
+#define MVIT_POOL_MAX 1  /* MaxPool3d, -inf padding              */
+#define MVIT_POOL_AVG 2  /* AvgPool3d, count_include_pad=True     */
+
+/* epilogues of mvit_linear_fwd */
+#define MVIT_EPI_NONE 0
+#define MVIT_EPI_GELU 1 /* exact erf GELU (common.py:20 nn.GELU) */
+
+/* implementation selector of the GEMM / attention entry points */
+#define MVIT_IMPL_AUTO 0    /* bf16 -> tcgen05, f32 -> fp32 FMA kernels */
+#define MVIT_IMPL_SIMT 1    /* force the CUDA-core kernels (any dtype)  */
+#define MVIT_IMPL_TCGEN05 2 /* force tensor-core kernels (bf16 only)    */
+
+/* Library / build identification. */
+int mvit_abi_version(void);
+const char *mvit_last_error(void);
+/* 1 when the current device is sm_100 (B200); 0 otherwise; negative on CUDA error. */
+int mvit_device_supported(void);
+
+/*
+ * LayerNorm over the last dimension.   y[r,:] = (x[r,:]-mean)/sqrt(var+eps)*gamma+beta
+ * Replaces: norm1 / norm2 of MultiScaleBlock (attention.py:421,436; eps 1e-6) and MViT.norm
+ * (video_model_builder.py:1249).  Statistics in fp32, biased variance (torch semantics).
+ */
+int mvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y,
+                       int64_t rows, int channels, float eps, int dtype, void *stream);
+
+/*
+ * Linear with fused epilogue.   y[M,N] = epi(x[M,K] · w[N,K]^T + bias[N]) (+ residual[M,N])
+ * Replaces: qkv / proj (attention.py:231,281), proj_max_pool / proj (attention.py:426,443),
+ * Mlp.fc1+GELU / fc2 (common.py:27-31) and the residual adds of attention.py:434,445, which are
+ * folded into the producing GEMM as `residual` (+ per-sample DropPath scale `row_scale`).
+ *   bias, residual, row_scale may be NULL.  row_scale[b] multiplies (x·wᵀ+bias) for rows
+ *   [b*rows_per_sample, (b+1)*rows_per_sample) BEFORE the residual is added (common.py:46-59).
+ *   ldy / ldr: leading dimensions (elements) of y and residual (>= N).
+ */
+int mvit_linear_fwd(const void *x, const void *w, const float *bias, const void *residual,
+                    const float *row_scale, int64_t rows_per_sample, void *y, int64_t M, int N,
+                    int K, int64_t ldy, int64_t ldr, int epilogue, int dtype, int impl, void *stream);
+
+/*
+ * attention_pool (attention.py:12-83) fused with its LayerNorm (attention.py:66-67).
+ *
+ * Input: a strided view of tokens  in[b, l, head, c]  at  in + b*in_bs + l*in_ls + head*in_hs + c
+ * (element strides).  This reads q, k or v straight out of the qkv Linear output
+ * [B, N, 3, heads, d] (attention.py:231-236) without the channels-first copy of attention.py:34-36,
+ * and equally a plain [B, L, C] tensor (heads = C/d, in_hs = d) for the skip path (attention.py:427).
+ * Output: out[b, l', head, c] at out + b*out_bs + l'*out_ls + head*out_hs + c.
+ *   mode      MVIT_POOL_*; `weight` = [d, kt*kh*kw] fp32 for CONV (Conv3d weight [d,1,kt,kh,kw]), else NULL
+ *   gamma/beta/eps  LayerNorm over d after pooling (NULL = none; eps 1e-5 on this path)
+ *   has_cls   first token bypasses pooling and joins the LayerNorm (attention.py:28-29, 62-64)
+ *   padding is k/2 per axis, ceil_mode = False:  T' = (T + 2*(kt/2) - kt)/st + 1, etc.
+ */
+int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
+                            const float *weight, const float *gamma, const float *beta, void *out,
+                            int64_t out_bs, int64_t out_ls, int64_t out_hs, int B, int heads, int d,
+                            int T, int H, int W, int kt, int kh, int kw, int st, int sh, int sw,
+                            int mode, int has_cls, float eps, int dtype, void *stream);
+
+/*
+ * Pooling attention core (attention.py:267-279):
+ *   out[b, i, head, :] = softmax_j( q[b,head,i,:]·k[b,head,j,:] * scale ) · v[b,head,j,:]  (+ q[b,head,i,:])
+ * q: [B, heads, Lq, d], k/v: [B, heads, Lk, d] contiguous; out: [B, Lq, heads*d] (the head-merge copy of
+ * attention.py:276 is folded into the store).  d must be 96.  The [Lq, Lk] score matrix is never
+ * written to memory.  lse (optional, fp32 [B, heads, Lq]) receives log-sum-exp of the scaled scores.
+ */
+int mvit_attention_fwd(const void *q, const void *k, const void *v, void *out, float *lse, int B,
+                       int heads, int Lq, int Lk, int d, float scale, int add_q_residual, int dtype,
+                       int impl, void *stream);
+
+/*
+ * Separable positional embedding add (video_model_builder.py:1206-1223):
+ *   x[b, (t*HW + s), c] += pos_spatial[s, c] + pos_temporal[t, c]     (in place, fp32 tables)
+ * with an optional dtype conversion: `src` (fp32 or bf16 per src_dtype) -> `dst` (dtype).
+ */
+int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
+                       const float *pos_temporal, void *dst, int B, int T, int HW, int C, int dtype,
+                       void *stream);
+
+/*
+ * Token mean-pool + classification head (video_model_builder.py:1310-1314, head_helper.py:409-417):
+ *   feat[b,:] = mean_l x[b,l,:];  logits = feat·Wᵀ + bias;  probs = softmax(logits) when apply_softmax.
+ * x: [B, L, C] (dtype); w: [num_classes, C] fp32; outputs fp32.  feat_out may be NULL.
+ */
+int mvit_mean_head_fwd(const void *x, const float *w, const float *bias, float *feat_out,
+                       float *out, int B, int L, int C, int num_classes, int apply_softmax,
+                       int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVIT_B200_H_ */

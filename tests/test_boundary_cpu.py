@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library loads and exports what include/mvit_b200.h declares; the Python drop-in has
+the reference's state_dict layout; the product refuses to compute without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from aicity_action_b200 import _lib
+from aicity_action_b200.attention import MultiScaleAttention, MultiScaleBlock, attention_pool
+from aicity_action_b200.config import AICITY_PRESETS, aicity_cfg
+from aicity_action_b200.mvit import MViT, round_width
+from tests.golden.cases import MODEL_CASES, tiny_cfg_overrides
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mvit_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvit_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mvit_b200.h but missing from the .so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.mvit_abi_version() == 1
+
+
+def test_library_has_no_torch_dependency():
+    # a C ABI: the .so must not link against libtorch / libc10 / libpython
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out and "python" not in out, out
+
+
+def test_bad_arguments_are_rejected_before_launch():
+    lib = _lib.load()
+    rc = lib.mvit_layernorm_fwd(None, None, None, None, 4, 96, 1e-6, 0, None)
+    assert rc != 0 and b"null" in lib.mvit_last_error()
+    rc = lib.mvit_attention_fwd(1, 1, 1, 1, None, 1, 1, 8, 8, 64, 0.1, 0, 0, 0, None)
+    assert rc != 0 and b"head_dim" in lib.mvit_last_error()
+
+
+@pytest.mark.parametrize("c", MODEL_CASES, ids=lambda c: c["name"])
+def test_state_dict_layout_matches_reference(c, golden_index):
+    torch.manual_seed(0)
+    m = MViT(aicity_cfg(c["yaml"], tiny_cfg_overrides(c)))
+    ref_shapes = golden_index["model_shapes"][c["name"]]
+    mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(mine.keys()) == list(ref_shapes.keys())      # names AND registration order
+    assert mine == ref_shapes
+
+
+def test_presets_cover_the_six_reference_yamls():
+    assert len(AICITY_PRESETS) == 6
+    n = {k: sum(p.numel() for p in MViT(aicity_cfg(k)).parameters()) for k in
+         ("MVITV2_FULL_B_16x4_CONV", "MVITV2_FULL_B_16x4_CONV_448", "MVITV2_B_16x4_CONV", "MVITV2_FULL_B_32x3_CONV")}
+    # SURVEY.md Appendix A / §6 parameter counts measured on the reference
+    assert n["MVITV2_FULL_B_16x4_CONV"] == 34415538
+    assert n["MVITV2_FULL_B_16x4_CONV_448"] == 35318706
+    assert n["MVITV2_B_16x4_CONV"] == 34379346
+    assert n["MVITV2_FULL_B_32x3_CONV"] == 51000018
+
+
+def test_round_width():
+    assert round_width(96, 2.0, divisor=2) == 192 and round_width(1, 2.0) == 2 and round_width(96, 0) == 96
+
+
+def test_no_cpu_fallback():
+    blk = MultiScaleBlock(96, 96, 1, kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3], stride_q=[1, 1, 1],
+                          stride_kv=[1, 2, 2], has_cls_embed=False)
+    with pytest.raises(_lib.MvitLibraryError):
+        with torch.no_grad():
+            blk(torch.randn(1, 2 * 4 * 4, 96), [2, 4, 4])
+    with pytest.raises(_lib.MvitLibraryError):
+        attention_pool(torch.randn(1, 1, 32, 96), torch.nn.MaxPool3d([1, 3, 3], [1, 2, 2], [0, 1, 1]), [2, 4, 4],
+                       has_cls_embed=False)
+
+
+def test_module_attribute_parity():
+    a = MultiScaleAttention(96, num_heads=2, qkv_bias=True, kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3],
+                            stride_q=[1, 2, 2], stride_kv=[1, 4, 4], has_cls_embed=False, expand_channel=True,
+                            expand_to_dim=192)
+    assert [n for n, _ in a.named_parameters()] == [
+        "qkv.weight", "qkv.bias", "proj.weight", "proj.bias", "pool_q.weight", "norm_q.weight", "norm_q.bias",
+        "pool_k.weight", "norm_k.weight", "norm_k.bias", "pool_v.weight", "norm_v.weight", "norm_v.bias"]
+    assert a.pool_q.weight.shape == (96, 1, 3, 3, 3) and a.norm_q.eps == 1e-5 and abs(a.scale - 96 ** -0.5) < 1e-12
+    nopool = MultiScaleAttention(96, num_heads=1, kernel_q=(1, 1, 1), stride_q=(1, 1, 1))
+    assert nopool.pool_q is None and nopool.norm_q is None

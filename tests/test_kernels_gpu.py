@@ -1,0 +1,154 @@
+"""GPU parity of each C-ABI kernel against the CPU oracle on identical seeded inputs.
+
+Tolerances (north_star): fp32 within 1e-4, bf16 within 2e-2, both as ‖Δ‖∞/‖ref‖∞."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mvit_oracle as O
+from aicity_action_b200 import ops
+from aicity_action_b200._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05
+from tests.conftest import rel_inf
+from tests.golden.cases import POOL_CASES
+from tests.golden.synth import synth_input, synth_tensor
+from tests.test_oracle_golden import pool_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def dev(t, dtype=None):
+    t = t.cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def rounded(t, dtype):
+    """The oracle sees exactly the values the kernel sees (bf16-rounded inputs for the bf16 path)."""
+    return t.to(dtype).float()
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("C", [96, 192, 384, 768, 80])
+def test_layernorm(C, dtype):
+    x = rounded(synth_input(1, f"ln{C}", (3, 37, C)) * 2 + 0.5, dtype)
+    g, b = synth_tensor(1, "norm.weight", (C,)), synth_tensor(1, "norm.bias", (C,))
+    ref = F.layer_norm(x, (C,), g, b, 1e-6)
+    got = ops.layernorm(dev(x, dtype), dev(g), dev(b), 1e-6)
+    assert got.dtype == dtype and rel_inf(got, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("c", POOL_CASES, ids=lambda c: c["name"])
+def test_attention_pool_vs_golden(c, dtype, golden):
+    x, w, ln, _ = pool_oracle(c)
+    xr = rounded(x, dtype)
+    ref, thw = O.attention_pool(xr, c["thw"], mode=c["mode"], kernel=c["kernel"], stride=c["stride"], weight=w,
+                                has_cls=c["cls"], ln=ln)
+    xd = dev(xr, dtype)
+    lnd = None if ln is None else (dev(ln[0]), dev(ln[1]), ln[2])
+    if c["ndim"] == 4:
+        got, gthw = ops.attention_pool_heads(xd, c["thw"], c["kernel"], c["stride"], mode=c["mode"],
+                                             weight=None if w is None else dev(w), ln=lnd, has_cls=c["cls"])
+    else:
+        got, gthw = ops.attention_pool_tokens(xd, c["thw"], c["kernel"], c["stride"], mode=c["mode"],
+                                              has_cls=c["cls"])
+    assert gthw == thw == list(golden[c["name"] + ".thw"])
+    assert rel_inf(got, ref) < TOL[dtype]
+    if dtype == torch.float32:      # and directly against the reference-generated fixture
+        assert rel_inf(got, torch.from_numpy(golden[c["name"]])) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_attention_pool_reads_qkv_layout_in_place(dtype):
+    """q/k/v are pooled straight out of the [B, N, 3, h, d] GEMM output (strided view, no copy)."""
+    B, h, d, thw = 2, 2, 96, (4, 8, 8)
+    N = math.prod(thw)
+    qkv = rounded(synth_input(5, "qkv", (B, N, 3, h, d)), dtype)
+    w = synth_tensor(5, "pool_k.weight", (d, 1, 3, 3, 3))
+    g, b = synth_tensor(5, "norm_k.weight", (d,)), synth_tensor(5, "norm_k.bias", (d,))
+    qd = dev(qkv, dtype)
+    for which, stride in ((0, [1, 1, 1]), (1, [1, 2, 2]), (2, [1, 4, 4])):
+        view = qkv[:, :, which].permute(0, 2, 1, 3)
+        ref, _ = O.attention_pool(view, thw, mode="conv", kernel=[3, 3, 3], stride=stride, weight=w, ln=(g, b, 1e-5))
+        got, _ = ops.attention_pool_heads(qd[:, :, which].permute(0, 2, 1, 3), list(thw), [3, 3, 3], stride,
+                                          mode="conv", weight=dev(w), ln=(dev(g), dev(b), 1e-5))
+        assert rel_inf(got, ref) < TOL[dtype]
+
+
+def _impls(dtype):
+    return [IMPL_SIMT] if dtype == torch.float32 else [IMPL_SIMT, IMPL_AUTO]
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(200, 288, 96), (130, 96, 384), (257, 768, 192), (64, 3072, 768), (50, 18, 768),
+                                   (1000, 192, 96), (384, 1152, 384)])
+def test_linear(M, N, K, dtype):
+    x = rounded(synth_input(2, f"x{M}{N}{K}", (M, K)), dtype)
+    w = rounded(synth_input(2, f"w{M}{N}{K}", (N, K)) / K ** 0.5, dtype)
+    bias = synth_input(2, "b", (N,)) * 0.1
+    res = rounded(synth_input(2, "r", (M, N)), dtype)
+    scale = torch.tensor([0.0, 1.25])
+    for impl in _impls(dtype):
+        for gelu, use_res, use_scale in [(False, False, False), (True, False, False), (False, True, False),
+                                         (False, True, True)]:
+            if use_scale and M % 2:
+                continue
+            ref = F.linear(x, w, bias)
+            if gelu:
+                ref = F.gelu(ref)
+            if use_scale:
+                ref = ref * scale.repeat_interleave(M // 2)[:, None]
+            if use_res:
+                ref = ref + res
+            got = ops.linear(dev(x, dtype), dev(w, dtype), dev(bias), residual=dev(res, dtype) if use_res else None,
+                             row_scale=dev(scale) if use_scale else None, gelu=gelu, impl=impl)
+            assert rel_inf(got, ref) < TOL[dtype], (impl, gelu, use_res, use_scale)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,h,Lq,Lk", [(2, 2, 256, 64), (1, 4, 72, 72), (1, 1, 1024, 16), (2, 1, 130, 392),
+                                       (1, 2, 392, 1568), (1, 8, 33, 257)])
+def test_attention(B, h, Lq, Lk, dtype):
+    d = 96
+    q = rounded(synth_input(3, f"q{Lq}", (B, h, Lq, d)), dtype)
+    k = rounded(synth_input(3, f"k{Lk}", (B, h, Lk, d)), dtype)
+    v = rounded(synth_input(3, f"v{Lk}", (B, h, Lk, d)), dtype)
+    scale = d ** -0.5
+    s = (q @ k.transpose(-2, -1)) * scale
+    ref_lse = torch.logsumexp(s, dim=-1)
+    o = s.softmax(-1) @ v
+    for impl in _impls(dtype):
+        for add_q in (True, False):
+            ref = (o + q if add_q else o).transpose(1, 2).reshape(B, Lq, h * d)
+            got, lse = ops.attention(dev(q, dtype), dev(k, dtype), dev(v, dtype), scale, add_q, want_lse=True,
+                                     impl=impl)
+            assert rel_inf(got, ref) < TOL[dtype], (impl, add_q)
+            assert rel_inf(lse, ref_lse) < 1e-3, (impl, add_q)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_pos_embed_and_head(dtype):
+    B, T, HW, C = 2, 4, 36, 96
+    tok = rounded(synth_input(4, "tok", (B, T * HW, C)), dtype)
+    ps, pt = synth_input(4, "ps", (1, HW, C)), synth_input(4, "pt", (1, T, C))
+    ref = tok + ps.repeat(1, T, 1) + torch.repeat_interleave(pt, HW, dim=1)
+    got = ops.pos_embed_add(dev(tok, dtype), dev(ps), dev(pt), T, dtype)
+    assert rel_inf(got, ref) < TOL[dtype]
+    x = rounded(synth_input(4, "feat", (B, 50, 768)), dtype)
+    w, b = synth_input(4, "hw", (18, 768)) * 0.05, synth_input(4, "hb", (18,))
+    logits = F.linear(x.mean(1), w, b)
+    assert rel_inf(ops.mean_head(dev(x, dtype), dev(w), dev(b), softmax=True), logits.softmax(1)) < TOL[dtype]
+    assert rel_inf(ops.mean_head(dev(x, dtype), dev(w), dev(b), softmax=False), logits) < TOL[dtype]
+
+
+def test_unsupported_requests_fail_loudly():
+    from aicity_action_b200._lib import MvitLibraryError
+    x = torch.randn(4, 96, device="cuda", dtype=torch.float16)
+    with pytest.raises(TypeError):
+        ops.layernorm(x, torch.ones(96, device="cuda"), torch.zeros(96, device="cuda"), 1e-6)
+    q = torch.randn(1, 1, 8, 64, device="cuda")
+    with pytest.raises(MvitLibraryError):
+        ops.attention(q, q, q, 0.1, False)
