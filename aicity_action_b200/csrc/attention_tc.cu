@@ -1,5 +1,320 @@
+// Fused pooling attention for sm_100a: out = softmax(q·kᵀ·scale)·v (+ q), head_dim 96, bf16 in/out.
+//
+// Replaces attention.py:267-279 (bmm, *scale, softmax, bmm, transpose/reshape, +q): the [Lq, Lk] score
+// matrix lives only in tensor memory.  One CTA owns 256 query rows of one (batch, head) — two 128-row
+// tiles that share every K/V tile it streams — and runs five kinds of warps:
+//   warp 0      TMA producer: Q (once) and a 3-stage ring of K/V tiles, 64B-swizzled 32-column boxes;
+//   warp 1      MMA issuer (one lane): S_i = Q_i·Kᵀ (tcgen05.mma SS, M=128 N=128 K=16 x6) into TMEM and
+//               O_i += P_i·V (tcgen05.mma TS: P from TMEM, V MN-major from smem, N=96 K=16 x8), ordered
+//               QK0(j) PV1(j-1) QK1(j) PV0(j) so one tile's softmax overlaps the other tile's MMAs;
+//   warp 2      TMEM allocator (512 columns: S0 | S1 | O0 | O1);
+//   warps 4-7   softmax of tile 0, warps 8-11 softmax of tile 1: thread = query row (TMEM lane); reads
+//               S with tcgen05.ld, online softmax in the exp2 domain with lazy rescaling (O is only
+//               rescaled when a row maximum grows by more than 2^8), writes P (bf16) over S with
+//               tcgen05.st, and at the end normalises O, adds the pooled-q residual and stores
+//               [B, Lq, heads*96] directly (the head-merge transpose costs nothing).
 #include "attention.cuh"
+#include "tc_common.cuh"
+
 namespace mvit {
-bool attention_tc_supported(const AttnArgs &, const char **why) { *why = "not built yet"; return false; }
-int attention_tc(const AttnArgs &, cudaStream_t) { set_error("attention_tc: not built"); return -1; }
+using namespace tc;
+
+namespace attn {
+constexpr int BQ = 128, BKV = 128, D = 96;
+constexpr int kChunkCols = 32, kChunks = 3;
+constexpr int kChunkBytes = 128 * kChunkCols * 2;   // 8 KB: 128 rows x 64 B, SWIZZLE_64B
+constexpr int kTileBytes = kChunks * kChunkBytes;   // 24 KB
+constexpr int kStages = 3;
+constexpr int kThreads = 384;
+constexpr int kSmemBytes = 2 * kTileBytes + kStages * 2 * kTileBytes + 256 + 1024;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColS = 0, kColO = 256;          // S_i at 128*i, O_i at 256 + 96*i
+constexpr float kRescaleThreshold = 8.0f;           // log2 units
+
+struct Params {
+  const bf16 *q;
+  bf16 *out;
+  float *lse;
+  int heads, Lq, Lk, add_q;
+  float scale_log2;   // scale * log2(e)
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sQ = smem;                                  // [2][24 KB]
+  uint8_t *sKV = smem + 2 * kTileBytes;                // [stage][K 24 KB | V 24 KB]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * 2 * kTileBytes);
+  uint64_t *q_full = bars;                 // 1
+  uint64_t *k_full = bars + 1;             // kStages
+  uint64_t *v_full = k_full + kStages;     // kStages
+  uint64_t *kv_empty = v_full + kStages;   // kStages
+  uint64_t *s_full = kv_empty + kStages;   // 2
+  uint64_t *p_ready = s_full + 2;          // 2
+  uint64_t *o_done = p_ready + 2;          // 2
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * BQ);
+  const bool two = q0 + BQ < p.Lq;                     // second 128-row tile has at least one live row
+  const int nkv = (p.Lk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (warp == 0 && lane == 0) {
+      // -------------------------------------------------------------- TMA producer
+      const int ntile = two ? 2 : 1;
+      mbar_arrive_expect_tx(q_full, ntile * kTileBytes);
+      for (int i = 0; i < ntile; ++i)
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(sQ + i * kTileBytes + c * kChunkBytes, &tmap_q, q_full, c * kChunkCols, q0 + i * BQ, bh);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t *kdst = sKV + s * 2 * kTileBytes, *vdst = kdst + kTileBytes;
+        mbar_arrive_expect_tx(&k_full[s], kTileBytes);
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(kdst + c * kChunkBytes, &tmap_k, &k_full[s], c * kChunkCols, j * BKV, bh);
+        mbar_arrive_expect_tx(&v_full[s], kTileBytes);
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(vdst + c * kChunkBytes, &tmap_v, &v_full[s], c * kChunkCols, j * BKV, bh);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // -------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // A = P (TMEM),    B = V (MN-major)
+      const uint32_t sq = smem_u32(sQ), skv = smem_u32(sKV);
+      auto issue_qk = [&](int i, int s) {
+        const uint32_t a0 = sq + i * kTileBytes, b0 = skv + s * 2 * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 1) * kChunkBytes + (k & 1) * 32;
+          umma_ss(tmem_base + kColS + i * BKV, make_smem_desc(a0 + off, 16, 512, SWZ_64B),
+                  make_smem_desc(b0 + off, 16, 512, SWZ_64B), idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[i]);
+      };
+      auto issue_pv = [&](int i, int s, bool accumulate) {
+        const uint32_t v0 = skv + s * 2 * kTileBytes + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // V tile: [128 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
+          umma_ts(tmem_base + kColO + i * D, tmem_base + kColS + i * BKV + k * 8,
+                  make_smem_desc(v0 + k * 16 * 64, kChunkBytes, 512, SWZ_64B), idesc_pv, (accumulate || k != 0));
+        }
+        umma_commit(&o_done[i]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        mbar_wait(&k_full[s], ph);
+        tc_fence_after();
+        issue_qk(0, s);
+        if (two && j > 0) {
+          mbar_wait(&p_ready[1], (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, (j - 1) % kStages, j - 1 > 0);
+          umma_commit(&kv_empty[(j - 1) % kStages]);
+        }
+        if (two) issue_qk(1, s);
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(&p_ready[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, s, j > 0);
+        if (!two) umma_commit(&kv_empty[s]);
+      }
+      if (two) {
+        mbar_wait(&p_ready[1], (nkv - 1) & 1);
+        tc_fence_after();
+        issue_pv(1, (nkv - 1) % kStages, nkv - 1 > 0);
+        umma_commit(&kv_empty[(nkv - 1) % kStages]);
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ---------------------------------------------------------------- softmax warpgroups
+    const int i = (warp - 4) >> 2;                    // which 128-row tile
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may touch
+    if (i == 0 || two) {
+      const int row = q0 + i * BQ + quarter * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+      const uint32_t tS = tmem_base + lane_base + kColS + i * BKV;
+      const uint32_t tO = tmem_base + lane_base + kColO + i * D;
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&s_full[i], j & 1);
+        tc_fence_after();
+        uint32_t s[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+        tmem_ld_wait();
+        const int valid = p.Lk - j * BKV;             // >= 1
+        if (valid < BKV) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e >= valid) s[c][e] = 0xff800000u;   // -inf
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[c][e]));
+        const float m_tile = mx * p.scale_log2;
+        if (j == 0) {
+          m_used = m_tile;
+        } else {
+          const float m_new = fmaxf(m_used, m_tile);
+          const bool need = (m_new - m_used) > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(&o_done[i], (j - 1) & 1);       // PV(j-1) has landed in O
+            tc_fence_after();
+            const float alpha = exp2f(m_used - m_new);
+            l_run *= alpha;
+            m_used = m_new;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        // P = exp2(s*scale_log2 - m_used), bf16-packed in place over S columns [0, 64)
+        float psum = 0.f;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int c = hlf * 2 + (e >> 4), idx = (e & 15) * 2;
+            const float p0 = exp2f(fmaf(__uint_as_float(s[c][idx]), p.scale_log2, -m_used));
+            const float p1 = exp2f(fmaf(__uint_as_float(s[c][idx + 1]), p.scale_log2, -m_used));
+            psum += p0 + p1;
+            __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            pk[e] = *reinterpret_cast<uint32_t *>(&h);
+          }
+          tmem_st32(tS + hlf * 32, pk);
+        }
+        l_run += psum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[i]);
+      }
+      // ---- epilogue: O / l (+ q) -> out[b, row, head*96 + :]
+      mbar_wait(&o_done[i], (nkv - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      const int b = bh / p.heads, head = bh % p.heads;
+      const bool live = row < p.Lq;
+      const bf16 *qrow = p.q + ((int64_t)bh * p.Lq + row) * D;
+      bf16 *orow = p.out + (((int64_t)b * p.Lq + row) * p.heads + head) * D;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint32_t w[4];
+            uint4 qv = make_uint4(0, 0, 0, 0);
+            if (p.add_q) qv = *reinterpret_cast<const uint4 *>(qrow + c * 32 + v4 * 8);
+            const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float lo = __uint_as_float(o[v4 * 8 + 2 * e]) * inv;
+              float hi = __uint_as_float(o[v4 * 8 + 2 * e + 1]) * inv;
+              lo += __uint_as_float(qw[e] << 16);
+              hi += __uint_as_float(qw[e] & 0xffff0000u);
+              __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+              w[e] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            *reinterpret_cast<uint4 *>(orow + c * 32 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      if (p.lse && live) p.lse[(int64_t)bh * p.Lq + row] = (m_used + log2f(l_run)) * 0.69314718055994530942f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace attn
+
+bool attention_tc_supported(const AttnArgs &a, const char **why) {
+  auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) { *why = "pointers must be 16-byte aligned"; return false; }
+  if ((int64_t)a.B * a.heads >= 65536) { *why = "B*heads too large"; return false; }
+  return true;
+}
+
+int attention_tc(const AttnArgs &a, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  const int BH = a.B * a.heads;
+  auto enc = [&](CUtensorMap *m, const void *ptr, int L) {
+    const uint64_t dims[3] = {(uint64_t)attn::D, (uint64_t)L, (uint64_t)BH};
+    const uint64_t strides[2] = {(uint64_t)attn::D * 2, (uint64_t)L * attn::D * 2};
+    const uint32_t box[3] = {attn::kChunkCols, 128, 1};
+    return encode_tmap_bf16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  };
+  int r;
+  if ((r = enc(&tq, a.q, a.Lq))) return r;
+  if ((r = enc(&tk, a.k, a.Lk))) return r;
+  if ((r = enc(&tv, a.v, a.Lk))) return r;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      attn::kSmemBytes));
+    attr_done = true;
+  }
+  attn::Params p{static_cast<const bf16 *>(a.q), static_cast<bf16 *>(a.out), a.lse, a.heads, a.Lq, a.Lk, a.add_q,
+                 a.scale * 1.44269504088896340736f};
+  dim3 grid((unsigned)((a.Lq + 2 * attn::BQ - 1) / (2 * attn::BQ)), (unsigned)BH);
+  attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
+  MVIT_LAUNCH_OK("attention(tcgen05)");
+  return 0;
+}
+
 }  // namespace mvit
