@@ -56,6 +56,23 @@ __global__ void __launch_bounds__(256) mean_head_kernel(const T *__restrict__ x,
   }
 }
 
+
+// uint8 THWC -> normalised CTHW (module_wrapper.py:332-346: /255, transpose, (x-mean)/std)
+template <typename T>
+__global__ void preprocess_u8_kernel(const uint8_t *__restrict__ in, T *__restrict__ out, int64_t pixels_per_clip,
+                                     int64_t total_pixels, float mean, float stdv) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pixels; i += stride) {
+    const int64_t b = i / pixels_per_clip, pix = i - b * pixels_per_clip;
+    const uint8_t *px = in + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[c], 255.0f), mean), stdv);
+      out[(b * 3 + c) * pixels_per_clip + pix] = from_f32<T>(v);
+    }
+  }
+}
+
 }  // namespace mvit
 
 extern "C" int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
@@ -98,5 +115,24 @@ extern "C" int mvit_mean_head_fwd(const void *x, const float *w, const float *bi
     mean_head_kernel<bf16><<<B, 256, smem, st>>>(static_cast<const bf16 *>(x), w, bias, feat_out, out, L, C, num_classes, apply_softmax);
   else MVIT_REQUIRE(false, "mean_head: unknown dtype");
   MVIT_LAUNCH_OK("mean_head");
+  return 0;
+}
+
+extern "C" int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, int T, int H, int W, float mean,
+                                      float stdv, int dtype, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(frames && clip, "preprocess: null pointer");
+  MVIT_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && stdv != 0.f, "preprocess: bad arguments");
+  if (B == 0) return 0;
+  const int64_t ppc = (int64_t)T * H * W, total = ppc * B;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + threads - 1) / threads, (int64_t)num_sms() * 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MVIT_F32)
+    preprocess_u8_kernel<float><<<blocks, threads, 0, st>>>(frames, static_cast<float *>(clip), ppc, total, mean, stdv);
+  else if (dtype == MVIT_BF16)
+    preprocess_u8_kernel<bf16><<<blocks, threads, 0, st>>>(frames, static_cast<bf16 *>(clip), ppc, total, mean, stdv);
+  else MVIT_REQUIRE(false, "preprocess: unknown dtype");
+  MVIT_LAUNCH_OK("preprocess_u8");
   return 0;
 }

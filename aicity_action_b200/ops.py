@@ -20,6 +20,30 @@ POOL_MODES = {"conv": POOL_CONV, "max": POOL_MAX, "avg": POOL_AVG}
 # number of C-ABI kernel launches issued through this module (bench.py reports it as gpu_launches)
 launch_count = 0
 
+# Optional per-kernel timing: when `event_log` is a dict, every wrapper brackets its launch with CUDA
+# events recorded on the launching stream and appends (category, start, end, work) to event_log[cat].
+event_log = None
+
+
+class _Timed:
+    __slots__ = ("cat", "work", "ev0")
+
+    def __init__(self, cat, work=0.0):
+        self.cat, self.work, self.ev0 = cat, work, None
+
+    def __enter__(self):
+        if event_log is not None:
+            self.ev0 = torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev0 is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            event_log.setdefault(self.cat, []).append((self.ev0, ev1, self.work))
+        return False
+
 
 def _dt(t: torch.Tensor) -> int:
     try:
@@ -65,8 +89,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     rows = x.numel() // C
     y = torch.empty_like(x) if out is None else out
     gamma, beta = _f32c(gamma), _f32c(beta)
-    check(_lib.load().mvit_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, C, float(eps),
-                                         _dt(x), _stream()), "mvit_layernorm_fwd")
+    with _Timed("layernorm", 2.0 * x.numel() * x.element_size()):
+        check(_lib.load().mvit_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, C, float(eps),
+                                             _dt(x), _stream()), "mvit_layernorm_fwd")
     launch_count += 1
     return y
 
@@ -93,10 +118,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert M % row_scale.numel() == 0
         rows_per_sample = M // row_scale.numel()
     bias = _f32c(bias)
-    check(_lib.load().mvit_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(row_scale),
-                                      rows_per_sample, _ptr(y), M, N, K, N, N,
-                                      EPI_GELU if gelu else EPI_NONE, _dt(x), impl, _stream()),
-          "mvit_linear_fwd")
+    with _Timed("linear", 2.0 * M * N * K):
+        check(_lib.load().mvit_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(row_scale),
+                                          rows_per_sample, _ptr(y), M, N, K, N, N,
+                                          EPI_GELU if gelu else EPI_NONE, _dt(x), impl, _stream()),
+              "mvit_linear_fwd")
     launch_count += 1
     return y
 
@@ -114,11 +140,14 @@ def attention_pool_strided(src: torch.Tensor, src_offset: int, in_strides: Tuple
     if weight is not None:
         weight = weight.reshape(d, -1)
     base = src.data_ptr() + src_offset * src.element_size()
-    check(_lib.load().mvit_attention_pool_fwd(
-        base, in_strides[0], in_strides[1], in_strides[2], _ptr(weight), _ptr(gamma), _ptr(beta),
-        _ptr(out), out_strides[0], out_strides[1], out_strides[2], B, heads, d, T, H, W,
-        kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2], POOL_MODES[mode],
-        1 if has_cls else 0, float(eps), _dt(src), _stream()), "mvit_attention_pool_fwd")
+    # algorithmic bytes: every input element of this q/k/v (or skip) tensor read once + output written once
+    work = float(B * heads * d * T * H * W + out.numel()) * src.element_size()
+    with _Timed("pool_" + mode, work):
+        check(_lib.load().mvit_attention_pool_fwd(
+            base, in_strides[0], in_strides[1], in_strides[2], _ptr(weight), _ptr(gamma), _ptr(beta),
+            _ptr(out), out_strides[0], out_strides[1], out_strides[2], B, heads, d, T, H, W,
+            kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2], POOL_MODES[mode],
+            1 if has_cls else 0, float(eps), _dt(src), _stream()), "mvit_attention_pool_fwd")
     launch_count += 1
 
 
@@ -168,9 +197,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, a
     assert k.shape == (B, h, Lk, d) and v.shape == (B, h, Lk, d) and q.dtype == k.dtype == v.dtype
     out = torch.empty((B, Lq, h * d), dtype=q.dtype, device=q.device)
     lse = torch.empty((B, h, Lq), dtype=torch.float32, device=q.device) if want_lse else None
-    check(_lib.load().mvit_attention_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, h, Lq, Lk, d,
-                                         float(scale), 1 if add_q else 0, _dt(q), impl, _stream()),
-          "mvit_attention_fwd")
+    with _Timed("attention", 4.0 * B * h * Lq * Lk * d):
+        check(_lib.load().mvit_attention_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, h, Lq, Lk, d,
+                                             float(scale), 1 if add_q else 0, _dt(q), impl, _stream()),
+              "mvit_attention_fwd")
     launch_count += 1
     return (out, lse) if want_lse else out
 
@@ -206,3 +236,17 @@ def mean_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], so
                                          1 if softmax else 0, _dt(x), _stream()), "mvit_mean_head_fwd")
     launch_count += 1
     return (out, feat) if want_feat else out
+
+
+def preprocess_u8(frames: torch.Tensor, dtype: torch.dtype, mean: float = 0.45, std: float = 0.225) -> torch.Tensor:
+    """uint8 frames [B, T, H, W, 3] -> normalised clip [B, 3, T, H, W] (module_wrapper.py:326-346)."""
+    global launch_count
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.ndim == 5 and frames.shape[-1] == 3
+    frames = frames.contiguous()
+    B, T, H, W, _ = frames.shape
+    out = torch.empty((B, 3, T, H, W), dtype=dtype, device=frames.device)
+    check(_lib.load().mvit_preprocess_u8_fwd(_ptr(frames), _ptr(out), B, T, H, W, float(mean), float(std),
+                                             _DT[dtype], _stream()), "mvit_preprocess_u8_fwd")
+    launch_count += 1
+    return out

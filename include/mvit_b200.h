@@ -122,6 +122,15 @@ int mvit_mean_head_fwd(const void *x, const float *w, const float *bias, float *
                        float *out, int B, int L, int C, int num_classes, int apply_softmax,
                        int dtype, void *stream);
 
+/*
+ * Clip normalisation (scripts/module_wrapper.py:326-346): uint8 frames [B, T, H, W, 3] (RGB, already
+ * resized) -> float clip [B, 3, T, H, W]:  ((x / 255) - mean) / std  evaluated in fp32 with IEEE
+ * division and rounded once to `dtype`, i.e. bit-identical to the reference's NumPy float32 pipeline
+ * when dtype == MVIT_F32.  Lets the host upload 1 byte per sample instead of 4.
+ */
+int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, int T, int H, int W, float mean,
+                           float std, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

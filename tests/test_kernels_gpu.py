@@ -152,3 +152,18 @@ def test_unsupported_requests_fail_loudly():
     q = torch.randn(1, 1, 8, 64, device="cuda")
     with pytest.raises(MvitLibraryError):
         ops.attention(q, q, q, 0.1, False)
+
+
+def test_preprocess_u8_bit_exact_fp32():
+    """module_wrapper.py:332-346 in NumPy float32 == the device kernel, bit for bit."""
+    import numpy as np
+    g = torch.Generator().manual_seed(9)
+    fr = torch.randint(0, 256, (2, 4, 12, 10, 3), dtype=torch.uint8, generator=g)
+    x = fr.numpy().astype("float32")
+    x /= 255.0
+    x = x.transpose([0, 4, 1, 2, 3])
+    ref = (x - np.float32(0.45)) / np.float32(0.225)
+    got = ops.preprocess_u8(fr.cuda(), torch.float32).cpu().numpy()
+    assert np.array_equal(got, np.ascontiguousarray(ref))
+    got16 = ops.preprocess_u8(fr.cuda(), torch.bfloat16).float().cpu()
+    assert torch.equal(got16, torch.from_numpy(np.ascontiguousarray(ref)).bfloat16().float())
