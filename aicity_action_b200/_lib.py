@@ -31,7 +31,8 @@ SIGNATURES = {
                                 + [_f, _i, _p]),
     "mvit_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
     "mvit_pos_embed_add": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "mvit_mean_head_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mvit_mean_head_workspace_floats": (C.c_size_t, [_i, _i, _i]),
+    "mvit_mean_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mvit_preprocess_u8_fwd": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _p]),
 }
 

@@ -18,9 +18,26 @@ __global__ void pos_embed_add_kernel(const TS *__restrict__ src, const float *__
   }
 }
 
-// one CTA per sample: feat = mean over tokens, logits = feat·Wᵀ + b, optional softmax
+// stage 1 (optional): partial[b][chunk][c] = sum of x over a chunk of kHeadChunk tokens (coalesced over c)
+constexpr int kHeadChunk = 32;
 template <typename T>
-__global__ void __launch_bounds__(256) mean_head_kernel(const T *__restrict__ x, const float *__restrict__ w,
+__global__ void __launch_bounds__(256) token_partial_sum_kernel(const T *__restrict__ x, float *__restrict__ partial,
+                                                                int L, int C, int chunks) {
+  const int b = blockIdx.y, ck = blockIdx.x;
+  const int l0 = ck * kHeadChunk, l1 = min(l0 + kHeadChunk, L);
+  const T *px = x + (int64_t)b * L * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = l0; l < l1; ++l) s += to_f32(px[(int64_t)l * C + c]);
+    partial[((int64_t)b * chunks + ck) * C + c] = s;
+  }
+}
+
+// one CTA per sample: feat = mean over tokens (or over the stage-1 partial sums), logits = feat·Wᵀ + b,
+// optional softmax.  Summation order is fixed (no atomics) so results are run-to-run reproducible.
+template <typename T>
+__global__ void __launch_bounds__(256) mean_head_kernel(const T *__restrict__ x, const float *__restrict__ partial,
+                                                        int chunks, const float *__restrict__ w,
                                                         const float *__restrict__ bias,
                                                         float *__restrict__ feat_out, float *__restrict__ out,
                                                         int L, int C, int NCLS, int apply_softmax) {
@@ -30,7 +47,11 @@ __global__ void __launch_bounds__(256) mean_head_kernel(const T *__restrict__ x,
   const T *px = x + (int64_t)b * L * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int l = 0; l < L; ++l) s += to_f32(px[(int64_t)l * C + c]);
+    if (partial) {
+      for (int k = 0; k < chunks; ++k) s += partial[((int64_t)b * chunks + k) * C + c];
+    } else {
+      for (int l = 0; l < L; ++l) s += to_f32(px[(int64_t)l * C + c]);
+    }
     feat[c] = s / (float)L;
     if (feat_out) feat_out[(int64_t)b * C + c] = feat[c];
   }
@@ -55,7 +76,6 @@ __global__ void __launch_bounds__(256) mean_head_kernel(const T *__restrict__ x,
     }
   }
 }
-
 
 // uint8 THWC -> normalised CTHW (module_wrapper.py:332-346: /255, transpose, (x-mean)/std)
 template <typename T>
@@ -99,21 +119,30 @@ extern "C" int mvit_pos_embed_add(const void *src, int src_dtype, const float *p
   return 0;
 }
 
+extern "C" size_t mvit_mean_head_workspace_floats(int B, int L, int C) {
+  return (size_t)B * ((L + mvit::kHeadChunk - 1) / mvit::kHeadChunk) * C;
+}
+
 extern "C" int mvit_mean_head_fwd(const void *x, const float *w, const float *bias, float *feat_out,
-                                  float *out, int B, int L, int C, int num_classes, int apply_softmax,
-                                  int dtype, void *stream) {
+                                  float *out, float *workspace, int B, int L, int C, int num_classes,
+                                  int apply_softmax, int dtype, void *stream) {
   using namespace mvit;
   MVIT_REQUIRE(x && w && out, "mean_head: null pointer");
   MVIT_REQUIRE(B >= 0 && L > 0 && C > 0 && num_classes > 0, "mean_head: bad shape");
+  MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "mean_head: unknown dtype");
   if (B == 0) return 0;
   const size_t smem = (size_t)(C + num_classes) * sizeof(float);
   MVIT_REQUIRE(smem <= 48 * 1024, "mean_head: C + classes too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == MVIT_F32)
-    mean_head_kernel<float><<<B, 256, smem, st>>>(static_cast<const float *>(x), w, bias, feat_out, out, L, C, num_classes, apply_softmax);
-  else if (dtype == MVIT_BF16)
-    mean_head_kernel<bf16><<<B, 256, smem, st>>>(static_cast<const bf16 *>(x), w, bias, feat_out, out, L, C, num_classes, apply_softmax);
-  else MVIT_REQUIRE(false, "mean_head: unknown dtype");
+  const int chunks = (L + kHeadChunk - 1) / kHeadChunk;
+  const bool two_stage = workspace != nullptr && chunks > 1;
+  if (dtype == MVIT_F32) {
+    if (two_stage) token_partial_sum_kernel<float><<<dim3(chunks, B), 256, 0, st>>>(static_cast<const float *>(x), workspace, L, C, chunks);
+    mean_head_kernel<float><<<B, 256, smem, st>>>(static_cast<const float *>(x), two_stage ? workspace : nullptr, chunks, w, bias, feat_out, out, L, C, num_classes, apply_softmax);
+  } else {
+    if (two_stage) token_partial_sum_kernel<bf16><<<dim3(chunks, B), 256, 0, st>>>(static_cast<const bf16 *>(x), workspace, L, C, chunks);
+    mean_head_kernel<bf16><<<B, 256, smem, st>>>(static_cast<const bf16 *>(x), two_stage ? workspace : nullptr, chunks, w, bias, feat_out, out, L, C, num_classes, apply_softmax);
+  }
   MVIT_LAUNCH_OK("mean_head");
   return 0;
 }

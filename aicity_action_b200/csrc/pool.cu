@@ -5,16 +5,9 @@
 // Generic kernel (any kernel size / stride / d % 32 == 0, cls token, three modes): one warp per output
 // token*head, lane owns channels {lane, lane+32, ...} so every global access of a warp is one contiguous
 // d*sizeof(T) segment.  The tuned stride-(1,s,s) 3x3x3 path lives in pool_tiled.cu.
-#include "common.cuh"
+#include "pool.cuh"
 
 namespace mvit {
-
-struct PoolParams {
-  int64_t in_bs, in_ls, in_hs, out_bs, out_ls, out_hs;
-  int B, heads, d, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo;
-  int has_cls, has_ln;
-  float eps;
-};
 
 template <typename T, int NC, int MODE>
 __global__ void __launch_bounds__(256) pool_generic_kernel(const T *__restrict__ in,
@@ -132,10 +125,6 @@ static int dispatch_generic(const void *in, const float *w, const float *g, cons
   }
   MVIT_REQUIRE(false, "attention_pool: head_dim %d unsupported (need 32..128, multiple of 32)", p.d);
 }
-
-// tuned path (pool_tiled.cu); returns 1 if it does not apply
-int pool_tiled_try(const void *in, const float *w, const float *g, const float *b, void *out,
-                   const PoolParams &p, int mode, int dtype, cudaStream_t st);
 
 }  // namespace mvit
 

@@ -1,0 +1,17 @@
+#pragma once
+#include "common.cuh"
+
+namespace mvit {
+
+struct PoolParams {
+  int64_t in_bs, in_ls, in_hs, out_bs, out_ls, out_hs;
+  int B, heads, d, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo;
+  int has_cls, has_ln;
+  float eps;
+};
+
+// tuned path (pool_tiled.cu); returns 1 if it does not apply, 0 on launch, <0 on error
+int pool_tiled_try(const void *in, const float *w, const float *g, const float *b, void *out,
+                   const PoolParams &p, int mode, int dtype, cudaStream_t st);
+
+}  // namespace mvit

@@ -1,11 +1,263 @@
-// Tuned attention_pool path (3x3x3 depthwise conv, stride (1,s,s), d = 96) — see DESIGN.md §kernels.
-#include "common.cuh"
+// Tuned attention_pool: depthwise 3x3x3 Conv3d, stride (1,s,s), pad 1, head_dim 96, fused LayerNorm.
+// (attention.py:172-212 pool_{q,k,v} + attention.py:66-67 norm_{q,k,v}; HBM-bound)
+//
+// A CTA owns one (batch, head), a TH x 8 tile of output positions and a range of output frames, and
+// marches through the input frames it needs ONCE: each frame's halo tile is brought into shared
+// memory with 16-byte cp.async (zero-filled outside the image), double-buffered against the math.
+// A warp owns CPW consecutive output columns of one output row; lane L owns channels {2L, 2L+1, 64+L}
+// (one 4-byte + one 2-byte shared load per input position, conflict-free).  The 27x3 filter taps of
+// those channels live in registers.  An input frame t contributes to outputs t-1, t, t+1 through three
+// rolling accumulator sets, so every input value is loaded from shared memory once per row it
+// touches and reused across the kw taps of neighbouring columns.  FMAs on the channel pair use the
+// packed fp32x2 FMA of sm_100 (bit-identical to two fmaf).  When a frame completes, the warp
+// LayerNorms the 96 channels of each of its columns (fp32 statistics, shuffles) and stores 192
+// contiguous bytes per token*head.
+#include "pool.cuh"
 
 namespace mvit {
-struct PoolParams;
-// returns 1 when the tuned path does not apply (caller falls through to the generic CUDA kernel)
-int pool_tiled_try(const void *, const float *, const float *, const float *, void *,
-                   const PoolParams &, int, int, cudaStream_t) {
+namespace ptile {
+
+constexpr int TW = 8;
+constexpr int kThreads = 256;
+
+template <typename T> struct IO;
+template <> struct IO<bf16> {
+  static constexpr int kPitch = 192;  // bytes per position
+  __device__ __forceinline__ static void load3(const uint8_t *pos, int lane, float2 &xy, float &z) {
+    const uint32_t u = *reinterpret_cast<const uint32_t *>(pos + 4 * lane);
+    xy.x = __uint_as_float(u << 16);
+    xy.y = __uint_as_float(u & 0xffff0000u);
+    z = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(pos + 128 + 2 * lane)) << 16);
+  }
+  __device__ __forceinline__ static void store3(bf16 *row, int lane, float2 xy, float z) {
+    *reinterpret_cast<__nv_bfloat162 *>(row + 2 * lane) = __floats2bfloat162_rn(xy.x, xy.y);
+    row[64 + lane] = __float2bfloat16_rn(z);
+  }
+};
+template <> struct IO<float> {
+  static constexpr int kPitch = 384;
+  __device__ __forceinline__ static void load3(const uint8_t *pos, int lane, float2 &xy, float &z) {
+    xy = *reinterpret_cast<const float2 *>(pos + 8 * lane);
+    z = *reinterpret_cast<const float *>(pos + 256 + 4 * lane);
+  }
+  __device__ __forceinline__ static void store3(float *row, int lane, float2 xy, float z) {
+    *reinterpret_cast<float2 *>(row + 2 * lane) = xy;
+    row[64 + lane] = z;
+  }
+};
+
+template <int S, int CPW> struct Geo {
+  static constexpr int MS = S < 3 ? S : 3;              // compact stride between neighbouring outputs
+  static constexpr int TH = CPW == 8 ? 8 : 4;           // 8 warps: one row each, or two warps per row
+  static constexpr int NR = (TH - 1) * MS + 3;          // compact input rows / cols of the halo tile
+  static constexpr int NC = (TW - 1) * MS + 3;
+  static constexpr int NPOS = NR * NC;
+  static constexpr int WC = (CPW - 1) * MS + 3;         // compact cols one warp touches
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(src_bytes)
+               : "memory");
+}
+
+template <typename T, int S, int CPW>
+__global__ void __launch_bounds__(kThreads, 1)
+pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, const float *__restrict__ gamma,
+                  const float *__restrict__ beta, T *__restrict__ out, PoolParams p, int tiles_w, int t_per_cta) {
+  using G = Geo<S, CPW>;
+  constexpr int PITCH = IO<T>::kPitch;
+  constexpr int CHUNKS = PITCH / 16;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t *buf0 = smem, *buf1 = smem + G::NPOS * PITCH;
+  int *offs = reinterpret_cast<int *>(smem + 2 * G::NPOS * PITCH);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_h = blockIdx.x / tiles_w, tile_w = blockIdx.x % tiles_w;
+  const int b = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
+  const int to0 = blockIdx.z * t_per_cta, to1 = min(to0 + t_per_cta, p.To);   // output frames [to0, to1)
+  const int ho0 = tile_h * G::TH, wo0 = tile_w * TW;
+
+  // per-position element offset inside one input frame (or -1 outside the image)
+  for (int i = threadIdx.x; i < G::NPOS; i += kThreads) {
+    const int r = i / G::NC, c = i % G::NC;
+    const int hin = ho0 * S - 1 + (S < 3 ? r : (r / 3) * S + r % 3);
+    const int win = wo0 * S - 1 + (S < 3 ? c : (c / 3) * S + c % 3);
+    offs[i] = (hin >= 0 && hin < p.H && win >= 0 && win < p.W) ? (int)((hin * p.W + win) * p.in_ls) : -1;
+  }
+  // filter taps of this lane's channels: w[tap] = {c=2L, c=2L+1}, wz[tap] = c=64+L
+  float2 wxy[27];
+  float wz[27];
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) {
+    wxy[tap].x = __ldg(weight + (2 * lane) * 27 + tap);
+    wxy[tap].y = __ldg(weight + (2 * lane + 1) * 27 + tap);
+    wz[tap] = __ldg(weight + (64 + lane) * 27 + tap);
+  }
+  float2 gxy = make_float2(1.f, 1.f), bxy = make_float2(0.f, 0.f);
+  float gz = 1.f, bz = 0.f;
+  if (p.has_ln) {
+    gxy = make_float2(__ldg(gamma + 2 * lane), __ldg(gamma + 2 * lane + 1));
+    bxy = make_float2(__ldg(beta + 2 * lane), __ldg(beta + 2 * lane + 1));
+    gz = __ldg(gamma + 64 + lane);
+    bz = __ldg(beta + 64 + lane);
+  }
+  __syncthreads();
+
+  const T *src_bh = in + (int64_t)b * p.in_bs + (int64_t)head * p.in_hs;
+  const int64_t frame_elems = (int64_t)p.H * p.W * p.in_ls;
+  auto load_frame = [&](int t, uint8_t *dst) {
+    const T *base = src_bh + t * frame_elems;
+    for (int i = threadIdx.x; i < G::NPOS * CHUNKS; i += kThreads) {
+      const int pos = i / CHUNKS, ch = i - pos * CHUNKS;
+      const int off = offs[pos];
+      const T *src = off >= 0 ? base + off + ch * (16 / (int)sizeof(T)) : base;
+      cp_async16(dst + pos * PITCH + ch * 16, src, off >= 0 ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int hl = CPW == 8 ? warp : (warp >> 1);          // output row of this warp inside the tile
+  const int cl0 = CPW == 8 ? 0 : (warp & 1) * 4;         // first output column of this warp
+  // rolling accumulators: a[0] -> output frame t-1, a[1] -> t, a[2] -> t+1 while input frame t is processed
+  float2 axy[3][CPW];
+  float az[3][CPW];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) { axy[k][j] = make_float2(0.f, 0.f); az[k][j] = 0.f; }
+
+  const int t_first = max(to0 - 1, 0), t_last = min(to1, p.T - 1);   // input frames needed (st == 1)
+  load_frame(t_first, buf0);
+  int cur = 0;
+  for (int t = t_first; t <= t_last; ++t) {
+    uint8_t *bufc = cur ? buf1 : buf0;
+    if (t + 1 <= t_last) {
+      load_frame(t + 1, cur ? buf0 : buf1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- accumulate this input frame into the three output frames it touches
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const uint8_t *rowp = bufc + ((hl * G::MS + kh) * G::NC + cl0 * G::MS) * PITCH;
+#pragma unroll
+      for (int cc = 0; cc < G::WC; ++cc) {
+        float2 xy;
+        float z;
+        IO<T>::load3(rowp + cc * PITCH, lane, xy, z);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          // which output column (if any) sees compact input col cc through tap kw
+          int j = -1;
+          if (S == 1) j = cc - kw;
+          else if (S == 2) j = ((cc - kw) % 2 == 0) ? (cc - kw) / 2 : -1;
+          else j = (cc % 3 == kw) ? cc / 3 : -1;
+          if (j >= 0 && j < CPW) {
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+              const int tap = (kt * 3 + kh) * 3 + kw;
+              // input frame t is tap kt of output frame t + 1 - kt  -> accumulator slot 2 - kt
+              axy[2 - kt][j] = __ffma2_rn(xy, wxy[tap], axy[2 - kt][j]);
+              az[2 - kt][j] = fmaf(z, wz[tap], az[2 - kt][j]);
+            }
+          }
+        }
+      }
+    }
+    // ---- output frame t-1 is complete (and frame t too when t is the last input frame)
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int to = pass == 0 ? t - 1 : t;
+      const bool emit = to >= to0 && to < to1 && (pass == 0 || t == p.T - 1);
+      if (emit) {
+        const int ho = ho0 + hl;
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          float2 v = pass == 0 ? axy[0][j] : axy[1][j];
+          float vz = pass == 0 ? az[0][j] : az[1][j];
+          if (p.has_ln) {
+            const float mean = warp_sum(v.x + v.y + vz) * (1.0f / 96.0f);
+            const float dx = v.x - mean, dy = v.y - mean, dz = vz - mean;
+            const float rstd = rsqrtf(warp_sum(dx * dx + dy * dy + dz * dz) * (1.0f / 96.0f) + p.eps);
+            v.x = dx * rstd * gxy.x + bxy.x;
+            v.y = dy * rstd * gxy.y + bxy.y;
+            vz = dz * rstd * gz + bz;
+          }
+          const int wo = wo0 + cl0 + j;
+          if (ho < p.Ho && wo < p.Wo) {
+            T *row = out + (int64_t)b * p.out_bs + (int64_t)((to * p.Ho + ho) * p.Wo + wo) * p.out_ls +
+                     (int64_t)head * p.out_hs;
+            IO<T>::store3(row, lane, v, vz);
+          }
+        }
+      }
+    }
+    // rotate: slot0 <- slot1 <- slot2 <- 0
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) {
+      axy[0][j] = axy[1][j]; az[0][j] = az[1][j];
+      axy[1][j] = axy[2][j]; az[1][j] = az[2][j];
+      axy[2][j] = make_float2(0.f, 0.f); az[2][j] = 0.f;
+    }
+    __syncthreads();   // everyone is done with bufc before the next iteration's prefetch overwrites it
+    cur ^= 1;
+  }
+}
+
+template <typename T, int S, int CPW>
+static int launch(const void *in, const float *w, const float *g, const float *b, void *out, const PoolParams &p,
+                  cudaStream_t st) {
+  using G = Geo<S, CPW>;
+  const size_t smem = 2 * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MVIT_CUDA_OK(cudaFuncSetAttribute(pool_tiled_kernel<T, S, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int tiles_h = (p.Ho + G::TH - 1) / G::TH, tiles_w = (p.Wo + TW - 1) / TW;
+  const int bh = p.B * p.heads;
+  // split the frame axis until the grid covers the GPU about twice (each split re-reads one halo frame)
+  int t_per_cta = p.To;
+  while (t_per_cta > 2 && (int64_t)tiles_h * tiles_w * bh * ((p.To + t_per_cta - 1) / t_per_cta) < 2 * num_sms())
+    t_per_cta = (t_per_cta + 1) / 2;
+  dim3 grid(tiles_h * tiles_w, bh, (p.To + t_per_cta - 1) / t_per_cta);
+  pool_tiled_kernel<T, S, CPW><<<grid, kThreads, smem, st>>>(static_cast<const T *>(in), w, g, b, static_cast<T *>(out),
+                                                             p, tiles_w, t_per_cta);
+  MVIT_LAUNCH_OK("attention_pool(tiled)");
+  return 0;
+}
+
+template <typename T>
+static int dispatch(const void *in, const float *w, const float *g, const float *b, void *out, const PoolParams &p,
+                    cudaStream_t st) {
+  switch (p.sh) {
+    case 1: return launch<T, 1, 8>(in, w, g, b, out, p, st);
+    case 2: return launch<T, 2, 4>(in, w, g, b, out, p, st);
+    case 4: return launch<T, 4, 4>(in, w, g, b, out, p, st);
+    case 8: return launch<T, 8, 4>(in, w, g, b, out, p, st);
+  }
   return 1;
 }
+
+}  // namespace ptile
+
+int pool_tiled_try(const void *in, const float *w, const float *g, const float *b, void *out, const PoolParams &p,
+                   int mode, int dtype, cudaStream_t st) {
+  if (mode != MVIT_POOL_CONV || p.d != 96 || p.has_cls) return 1;
+  if (p.kt != 3 || p.kh != 3 || p.kw != 3 || p.st != 1 || p.sh != p.sw) return 1;
+  if (p.sh != 1 && p.sh != 2 && p.sh != 4 && p.sh != 8) return 1;
+  if ((int64_t)p.B * p.heads >= 65536) return 1;
+  if ((int64_t)p.H * p.W * p.in_ls >= ((int64_t)1 << 31)) return 1;
+  // 16-byte cp.async needs aligned rows: every stride and the base must be multiples of 16 bytes
+  const int64_t es = dtype == MVIT_BF16 ? 2 : 4;
+  auto al = [&](int64_t elems) { return (elems * es) % 16 == 0; };
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || !al(p.in_bs) || !al(p.in_ls) || !al(p.in_hs)) return 1;
+  if ((reinterpret_cast<uintptr_t>(out) & 7) || (p.out_bs * es) % 8 || (p.out_ls * es) % 8 || (p.out_hs * es) % 8) return 1;
+  if (dtype == MVIT_BF16) return ptile::dispatch<bf16>(in, w, g, b, out, p, st);
+  return ptile::dispatch<float>(in, w, g, b, out, p, st);
+}
+
 }  // namespace mvit

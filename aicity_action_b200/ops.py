@@ -232,9 +232,11 @@ def mean_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], so
     n = w.shape[0]
     out = torch.empty((B, n), dtype=torch.float32, device=x.device)
     feat = torch.empty((B, Cc), dtype=torch.float32, device=x.device) if want_feat else None
-    check(_lib.load().mvit_mean_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(feat), _ptr(out), B, L, Cc, n,
-                                         1 if softmax else 0, _dt(x), _stream()), "mvit_mean_head_fwd")
-    launch_count += 1
+    lib = _lib.load()
+    ws = torch.empty((lib.mvit_mean_head_workspace_floats(B, L, Cc),), dtype=torch.float32, device=x.device)
+    check(lib.mvit_mean_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(feat), _ptr(out), _ptr(ws), B, L, Cc, n,
+                                 1 if softmax else 0, _dt(x), _stream()), "mvit_mean_head_fwd")
+    launch_count += 2 if L > 32 else 1
     return (out, feat) if want_feat else out
 
 

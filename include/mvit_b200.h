@@ -117,10 +117,13 @@ int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
  * Token mean-pool + classification head (video_model_builder.py:1310-1314, head_helper.py:409-417):
  *   feat[b,:] = mean_l x[b,l,:];  logits = feat·Wᵀ + bias;  probs = softmax(logits) when apply_softmax.
  * x: [B, L, C] (dtype); w: [num_classes, C] fp32; outputs fp32.  feat_out may be NULL.
+ * workspace: optional fp32 scratch of mvit_mean_head_workspace_floats(B, L, C) elements; with it the
+ * token sum runs as a grid-wide two-stage reduction (fixed order, no atomics) instead of one CTA per clip.
  */
+size_t mvit_mean_head_workspace_floats(int B, int L, int C);
 int mvit_mean_head_fwd(const void *x, const float *w, const float *bias, float *feat_out,
-                       float *out, int B, int L, int C, int num_classes, int apply_softmax,
-                       int dtype, void *stream);
+                       float *out, float *workspace, int B, int L, int C, int num_classes,
+                       int apply_softmax, int dtype, void *stream);
 
 /*
  * Clip normalisation (scripts/module_wrapper.py:326-346): uint8 frames [B, T, H, W, 3] (RGB, already
