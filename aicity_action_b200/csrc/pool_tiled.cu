@@ -1,9 +1,10 @@
 // Tuned attention_pool: depthwise 3x3x3 Conv3d, stride (1,s,s), pad 1, head_dim 96, fused LayerNorm.
 // (attention.py:172-212 pool_{q,k,v} + attention.py:66-67 norm_{q,k,v}; HBM-bound)
 //
-// A CTA owns one (batch, head), a TH x 8 tile of output positions and a range of output frames, and
-// marches through the input frames it needs ONCE: each frame's halo tile is brought into shared
-// memory with 16-byte cp.async (zero-filled outside the image), double-buffered against the math.
+// A CTA (4 warps, two resident per SM) owns one (batch, head), a TH x 8 tile of output positions and a
+// range of output frames, and marches through the input frames it needs ONCE: each frame's halo tile is
+// brought into shared memory with 16-byte cp.async (zero-filled outside the image) through a 3-4 deep
+// ring, so several frames per CTA are in flight and HBM latency is covered.
 // A warp owns CPW consecutive output columns of one output row; lane L owns channels {2L, 2L+1, 64+L}
 // (one 4-byte + one 2-byte shared load per input position, conflict-free).  The 27x3 filter taps of
 // those channels live in registers.  An input frame t contributes to outputs t-1, t, t+1 through three
@@ -18,7 +19,8 @@ namespace mvit {
 namespace ptile {
 
 constexpr int TW = 8;
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
 
 template <typename T> struct IO;
 template <> struct IO<bf16> {
@@ -48,7 +50,7 @@ template <> struct IO<float> {
 
 template <int S, int CPW> struct Geo {
   static constexpr int MS = S < 3 ? S : 3;              // compact stride between neighbouring outputs
-  static constexpr int TH = CPW == 8 ? 8 : 4;           // 8 warps: one row each, or two warps per row
+  static constexpr int TH = CPW == 8 ? kWarps : kWarps / 2;   // one warp per row, or two warps per row
   static constexpr int NR = (TH - 1) * MS + 3;          // compact input rows / cols of the halo tile
   static constexpr int NC = (TW - 1) * MS + 3;
   static constexpr int NPOS = NR * NC;
@@ -61,16 +63,20 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_b
                : "memory");
 }
 
+template <typename T> struct Ring { static constexpr int kStages = sizeof(T) == 2 ? 4 : 3; };
+
 template <typename T, int S, int CPW>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, const float *__restrict__ gamma,
                   const float *__restrict__ beta, T *__restrict__ out, PoolParams p, int tiles_w, int t_per_cta) {
   using G = Geo<S, CPW>;
   constexpr int PITCH = IO<T>::kPitch;
   constexpr int CHUNKS = PITCH / 16;
+  constexpr int kStages = Ring<T>::kStages;
+  constexpr int FRAME = G::NPOS * PITCH;
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t *buf0 = smem, *buf1 = smem + G::NPOS * PITCH;
-  int *offs = reinterpret_cast<int *>(smem + 2 * G::NPOS * PITCH);
+  int *offs = reinterpret_cast<int *>(smem + kStages * FRAME);
+  float *w_s = reinterpret_cast<float *>(offs + G::NPOS);   // [96][27] staged copy of the filter
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_h = blockIdx.x / tiles_w, tile_w = blockIdx.x % tiles_w;
@@ -85,14 +91,16 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
     const int win = wo0 * S - 1 + (S < 3 ? c : (c / 3) * S + c % 3);
     offs[i] = (hin >= 0 && hin < p.H && win >= 0 && win < p.W) ? (int)((hin * p.W + win) * p.in_ls) : -1;
   }
+  for (int i = threadIdx.x; i < 96 * 27; i += kThreads) w_s[i] = __ldg(weight + i);   // coalesced
+  __syncthreads();
   // filter taps of this lane's channels: w[tap] = {c=2L, c=2L+1}, wz[tap] = c=64+L
   float2 wxy[27];
   float wz[27];
 #pragma unroll
   for (int tap = 0; tap < 27; ++tap) {
-    wxy[tap].x = __ldg(weight + (2 * lane) * 27 + tap);
-    wxy[tap].y = __ldg(weight + (2 * lane + 1) * 27 + tap);
-    wz[tap] = __ldg(weight + (64 + lane) * 27 + tap);
+    wxy[tap].x = w_s[(2 * lane) * 27 + tap];
+    wxy[tap].y = w_s[(2 * lane + 1) * 27 + tap];
+    wz[tap] = w_s[(64 + lane) * 27 + tap];
   }
   float2 gxy = make_float2(1.f, 1.f), bxy = make_float2(0.f, 0.f);
   float gz = 1.f, bz = 0.f;
@@ -128,17 +136,23 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
     for (int j = 0; j < CPW; ++j) { axy[k][j] = make_float2(0.f, 0.f); az[k][j] = 0.f; }
 
   const int t_first = max(to0 - 1, 0), t_last = min(to1, p.T - 1);   // input frames needed (st == 1)
-  load_frame(t_first, buf0);
-  int cur = 0;
+  // ring prologue: frames t_first .. t_first+kStages-2 in flight (one commit group per frame, empty if past the end)
+#pragma unroll
+  for (int i = 0; i < kStages - 1; ++i) {
+    if (t_first + i <= t_last) load_frame(t_first + i, smem + i * FRAME);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int slot = 0;
   for (int t = t_first; t <= t_last; ++t) {
-    uint8_t *bufc = cur ? buf1 : buf0;
-    if (t + 1 <= t_last) {
-      load_frame(t + 1, cur ? buf0 : buf1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // groups committed so far: (t - t_first) + kStages - 1; frame t is the oldest that may be pending
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
+    __syncthreads();   // frame t visible to all warps; everyone finished frame t-1 -> its slot is free
+    {
+      const int tp = t + kStages - 1, sp = (slot + kStages - 1) % kStages;
+      if (tp <= t_last) load_frame(tp, smem + sp * FRAME);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __syncthreads();
+    uint8_t *bufc = smem + slot * FRAME;
     // ---- accumulate this input frame into the three output frames it touches
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -202,8 +216,7 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
       axy[1][j] = axy[2][j]; az[1][j] = az[2][j];
       axy[2][j] = make_float2(0.f, 0.f); az[2][j] = 0.f;
     }
-    __syncthreads();   // everyone is done with bufc before the next iteration's prefetch overwrites it
-    cur ^= 1;
+    slot = (slot + 1) % kStages;
   }
 }
 
@@ -211,7 +224,7 @@ template <typename T, int S, int CPW>
 static int launch(const void *in, const float *w, const float *g, const float *b, void *out, const PoolParams &p,
                   cudaStream_t st) {
   using G = Geo<S, CPW>;
-  const size_t smem = 2 * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS * sizeof(int);
+  const size_t smem = Ring<T>::kStages * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS * sizeof(int) + 96 * 27 * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     MVIT_CUDA_OK(cudaFuncSetAttribute(pool_tiled_kernel<T, S, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
