@@ -26,7 +26,8 @@ SIGNATURES = {
     "mvit_last_error": (C.c_char_p, []),
     "mvit_device_supported": (_i, []),
     "mvit_layernorm_fwd": (_i, [_p, _p, _p, _p, _i64, _i, _f, _i, _p]),
-    "mvit_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _i64, _i64, _i, _i, _i, _p]),
+    "mvit_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _i, _p]),
+    "mvit_im2col3d_fwd": (_i, [_p, _p] + [_i] * 16 + [_p]),
     "mvit_attention_pool_fwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64] + [_i] * 14
                                 + [_f, _i, _p]),
     "mvit_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p]),

@@ -31,6 +31,12 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColO = 256;          // S_i at 128*i, O_i at 256 + 96*i
 constexpr float kRescaleThreshold = 8.0f;           // log2 units
 
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, no range fix-ups
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Params {
   const bf16 *q;
   bf16 *out;
@@ -204,7 +210,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           if (__any_sync(0xffffffffu, need)) {
             mbar_wait(&o_done[i], (j - 1) & 1);       // PV(j-1) has landed in O
             tc_fence_after();
-            const float alpha = exp2f(m_used - m_new);
+            const float alpha = ex2_approx(m_used - m_new);
             l_run *= alpha;
             m_used = m_new;
 #pragma unroll
@@ -220,21 +226,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
         // P = exp2(s*scale_log2 - m_used), bf16-packed in place over S columns [0, 64)
-        float psum = 0.f;
+        const float2 c2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_used, -m_used);
+        float2 psum2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
           uint32_t pk[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int c = hlf * 2 + (e >> 4), idx = (e & 15) * 2;
-            const float p0 = exp2f(fmaf(__uint_as_float(s[c][idx]), p.scale_log2, -m_used));
-            const float p1 = exp2f(fmaf(__uint_as_float(s[c][idx + 1]), p.scale_log2, -m_used));
-            psum += p0 + p1;
-            __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][idx]), __uint_as_float(s[c][idx + 1])), c2, nm2);
+            const float2 pe = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            psum2 = __fadd2_rn(psum2, pe);
+            __nv_bfloat162 h = __floats2bfloat162_rn(pe.x, pe.y);
             pk[e] = *reinterpret_cast<uint32_t *>(&h);
           }
           tmem_st32(tS + hlf * 32, pk);
         }
+        const float psum = psum2.x + psum2.y;
         l_run += psum;
         tmem_st_wait();
         tc_fence_before();

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearArgs a) {
       float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
       if (a.epilogue == MVIT_EPI_GELU) v = gelu_erf(v);
       if (a.row_scale) v *= rs;
-      if (res) v += to_f32(res[m * a.ldr + n]);
+      if (res) v += to_f32(res[(a.res_period ? m % a.res_period : m) * a.ldr + n]);
       y[m * a.ldy + n] = from_f32<T>(v);
     }
   }
@@ -76,8 +76,8 @@ int linear_simt(const LinearArgs &a, int dtype, cudaStream_t st) {
 
 extern "C" int mvit_linear_fwd(const void *x, const void *w, const float *bias, const void *residual,
                                const float *row_scale, int64_t rows_per_sample, void *y, int64_t M,
-                               int N, int K, int64_t ldy, int64_t ldr, int epilogue, int dtype,
-                               int impl, void *stream) {
+                               int N, int K, int64_t ldy, int64_t ldr, int64_t residual_row_period,
+                               int epilogue, int dtype, int impl, void *stream) {
   using namespace mvit;
   MVIT_REQUIRE(x && w && y, "linear: null pointer");
   MVIT_REQUIRE(M >= 0 && N > 0 && K > 0, "linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
@@ -86,7 +86,8 @@ extern "C" int mvit_linear_fwd(const void *x, const void *w, const float *bias, 
   MVIT_REQUIRE(ldy >= N && (!residual || ldr >= N), "linear: leading dimension smaller than N");
   MVIT_REQUIRE(!row_scale || rows_per_sample > 0, "linear: row_scale needs rows_per_sample");
   if (M == 0) return 0;
-  LinearArgs a{x, w, residual, bias, row_scale, y, M, rows_per_sample, ldy, ldr, N, K, epilogue};
+  MVIT_REQUIRE(residual_row_period >= 0, "linear: negative residual_row_period");
+  LinearArgs a{x, w, residual, bias, row_scale, y, M, rows_per_sample, ldy, ldr, residual ? residual_row_period : 0, N, K, epilogue};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool use_tc = false;
   if (impl == MVIT_IMPL_TCGEN05 || (impl == MVIT_IMPL_AUTO && dtype == MVIT_BF16)) {

@@ -40,32 +40,30 @@ template <int BN> struct Cfg {
   static constexpr int kOutBytes = kBoxes * kBoxBytes;   // 48 KB / 24 KB
   static constexpr int kTmemCols = BN == 192 ? 512 : 256;
   static constexpr int kChunk = BN / 6;                  // columns per tcgen05.ld of one epilogue thread (32 / 16)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + BN * 4 + 512 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
 };
 
 struct Params {
   const float *bias, *row_scale;
-  int64_t M, rows_per_sample;
+  int64_t M, rows_per_sample, res_period;
   int N, K, epilogue, has_residual;
 };
 
-// GELU(x) = x * (0.5 + phi(x)),  phi(x) = 0.5*erf(x/sqrt2) ~ x * P(x^2) on |x| <= 4 (degree-8 minimax fit,
-// |gelu error| < 2e-5 there; saturated to +-0.5 outside).  FMA-pipe only, evaluated two values at a time.
+// GELU(x) = x * (0.5 + phi(x)),  phi(x) = 0.5*erf(x/sqrt2) ~ xc * P(xc^2) with xc = clamp(x, -4, 4) (degree-7 minimax
+// fit: |gelu error| < 9e-5 on [-4, 4] and < 5e-5*|x| outside, far below bf16 resolution).  FMA pipe only (no MUFU),
+// two values per instruction with the packed fp32x2 FMA of sm_100.
 __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   const float2 xc = make_float2(fminf(fmaxf(x.x, -4.f), 4.f), fminf(fmaxf(x.y, -4.f), 4.f));
   const float2 v = __fmul2_rn(xc, xc);
-  float2 r = make_float2(8.062082e-11f, 8.062082e-11f);
-  r = __ffma2_rn(r, v, make_float2(-7.002539e-09f, -7.002539e-09f));
-  r = __ffma2_rn(r, v, make_float2(2.7158907e-07f, 2.7158907e-07f));
-  r = __ffma2_rn(r, v, make_float2(-6.2945965e-06f, -6.2945965e-06f));
-  r = __ffma2_rn(r, v, make_float2(9.890462e-05f, 9.890462e-05f));
-  r = __ffma2_rn(r, v, make_float2(-0.0011339056f, -0.0011339056f));
-  r = __ffma2_rn(r, v, make_float2(0.009877438f, 0.009877438f));
-  r = __ffma2_rn(r, v, make_float2(-0.066410564f, -0.066410564f));
-  r = __ffma2_rn(r, v, make_float2(0.3989227f, 0.3989227f));
-  float2 phi = __fmul2_rn(r, xc);
-  phi.x = fabsf(x.x) >= 4.f ? copysignf(0.5f, x.x) : phi.x;
-  phi.y = fabsf(x.y) >= 4.f ? copysignf(0.5f, x.y) : phi.y;
+  float2 r = make_float2(-1.5806889130942636e-09f, -1.5806889130942636e-09f);
+  r = __ffma2_rn(r, v, make_float2(1.2170519880783104e-07f, 1.2170519880783104e-07f));
+  r = __ffma2_rn(r, v, make_float2(-4.100723799638217e-06f, -4.100723799638217e-06f));
+  r = __ffma2_rn(r, v, make_float2(8.066566078923643e-05f, 8.066566078923643e-05f));
+  r = __ffma2_rn(r, v, make_float2(-0.0010481934295967221f, -0.0010481934295967221f));
+  r = __ffma2_rn(r, v, make_float2(0.009664841927587986f, 0.009664841927587986f));
+  r = __ffma2_rn(r, v, make_float2(-0.06617535650730133f, -0.06617535650730133f));
+  r = __ffma2_rn(r, v, make_float2(0.3988475501537323f, 0.3988475501537323f));
+  const float2 phi = __fmul2_rn(r, xc);
   return __ffma2_rn(x, phi, __fmul2_rn(x, make_float2(0.5f, 0.5f)));
 }
 
@@ -80,7 +78,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint8_t *sB = smem + C::kStages * C::kABytes;
   uint8_t *sOut = smem + C::kStages * C::kStageBytes;
   float *sBias = reinterpret_cast<float *>(sOut + C::kNB * C::kOutBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + BN);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 2 * BN);   // sBias is double-buffered
   uint64_t *full = bars, *empty = full + C::kStages, *tfull = empty + C::kStages, *tempty = tfull + 2;
   uint64_t *res_full = tempty + 2, *buf_free = res_full + C::kNB;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(buf_free + C::kNB);
@@ -174,7 +172,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         mbar_wait(&buf_free[buf], phase ^ 1);         // the TMA store that last used this buffer has read it
         if (p.has_residual) {
-          const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * BN;
+          const int64_t mrow = (t / n_tiles) * BM;
+          const int m0 = (int)(p.res_period ? mrow % p.res_period : mrow), n0 = (int)(t % n_tiles) * BN;
           mbar_arrive_expect_tx(&res_full[buf], C::kOutBytes);
 #pragma unroll
           for (int bx = 0; bx < C::kBoxes; ++bx)
@@ -196,35 +195,48 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0, buf_phase = 0;
     int64_t it = 0;
+    // bias slice of the first tile; later slices are fetched one tile ahead (global latency off the critical path)
+    if (et < BN) {
+      const int n = (int)(blockIdx.x % n_tiles) * BN + et;
+      sBias[et] = (p.bias && blockIdx.x < tiles && n < p.N) ? p.bias[n] : 0.f;
+    }
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int64_t m0 = (t / n_tiles) * BM;
       const int n0 = (int)(t % n_tiles) * BN;
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile: sBias readers done, store issued
-      for (int i = et; i < BN; i += 256) sBias[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float *bias_s = sBias + (it & 1) * BN;
+      float bias_next = 0.f;
+      const int64_t tn = t + gridDim.x;
+      if (et < BN && tn < tiles && p.bias) {
+        const int n = (int)(tn % n_tiles) * BN + et;
+        if (n < p.N) bias_next = p.bias[n];
+      }
       float rs = 1.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + row, p.M - 1) / p.rows_per_sample];
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // this tile's bias slice is visible; previous store was issued
       mbar_wait(&res_full[buf], buf_phase);            // buffer is ours (and holds the residual tile, if any)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       uint8_t *obuf = sOut + buf * C::kOutBytes;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hf * (BN / 2);
+      uint32_t r[3][C::kChunk];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        uint32_t r[C::kChunk];
-        if constexpr (C::kChunk == 32) tmem_ld32(taddr + c * 32, r);
-        else tmem_ld16(taddr + c * 16, r);
-        tmem_ld_wait();
+        if constexpr (C::kChunk == 32) tmem_ld32(taddr + c * 32, r[c]);
+        else tmem_ld16(taddr + c * 16, r[c]);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
         const int col0 = hf * (BN / 2) + c * C::kChunk;          // first tile column of this chunk
 #pragma unroll
         for (int v = 0; v < C::kChunk / 8; ++v) {
           const int col = col0 + v * 8;
-          const float4 b0 = *reinterpret_cast<const float4 *>(sBias + col);
-          const float4 b1 = *reinterpret_cast<const float4 *>(sBias + col + 4);
-          float2 x[4] = {make_float2(__uint_as_float(r[v * 8 + 0]) + b0.x, __uint_as_float(r[v * 8 + 1]) + b0.y),
-                         make_float2(__uint_as_float(r[v * 8 + 2]) + b0.z, __uint_as_float(r[v * 8 + 3]) + b0.w),
-                         make_float2(__uint_as_float(r[v * 8 + 4]) + b1.x, __uint_as_float(r[v * 8 + 5]) + b1.y),
-                         make_float2(__uint_as_float(r[v * 8 + 6]) + b1.z, __uint_as_float(r[v * 8 + 7]) + b1.w)};
+          const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + col);
+          const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + col + 4);
+          float2 x[4] = {make_float2(__uint_as_float(r[c][v * 8 + 0]) + b0.x, __uint_as_float(r[c][v * 8 + 1]) + b0.y),
+                         make_float2(__uint_as_float(r[c][v * 8 + 2]) + b0.z, __uint_as_float(r[c][v * 8 + 3]) + b0.w),
+                         make_float2(__uint_as_float(r[c][v * 8 + 4]) + b1.x, __uint_as_float(r[c][v * 8 + 5]) + b1.y),
+                         make_float2(__uint_as_float(r[c][v * 8 + 6]) + b1.z, __uint_as_float(r[c][v * 8 + 7]) + b1.w)};
           if (p.epilogue == MVIT_EPI_GELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = gelu_fast2(x[j]);
@@ -253,6 +265,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           *slot = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+      if (et < BN) sBias[((it + 1) & 1) * BN + et] = bias_next;   // readers of that half finished a tile ago
       // accumulator fully read -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -323,6 +336,7 @@ bool linear_tc_supported(const LinearArgs &a, const char **why) {
   if (a.M >= ((int64_t)1 << 31)) { *why = "M too large"; return false; }
   auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al(a.x) || !al(a.w) || !al(a.y) || (a.residual && !al(a.residual))) { *why = "pointers must be 16-byte aligned"; return false; }
+  if (a.res_period % gemm::BM != 0) { *why = "residual_row_period must be a multiple of 128"; return false; }
   return true;
 }
 
@@ -342,7 +356,8 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   if ((r = enc2(&tw, a.w, a.K, a.N, a.K, gemm::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
   if ((r = enc2(&ty, a.y, a.N, a.M, a.ldy, gemm::kBoxCols, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
   if (a.residual) {
-    if ((r = enc2(&tr, a.residual, a.N, a.M, a.ldr, gemm::kBoxCols, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+    const uint64_t res_rows = a.res_period ? (uint64_t)a.res_period : (uint64_t)a.M;
+    if ((r = enc2(&tr, a.residual, a.N, res_rows, a.ldr, gemm::kBoxCols, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
   } else {
     tr = ty;
   }
@@ -351,7 +366,7 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
     MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
-  gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.N, a.K, a.epilogue, a.residual ? 1 : 0};
+  gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0};
   const int64_t tiles = ((a.M + gemm::BM - 1) / gemm::BM) * ((a.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
   gemm::linear_tc_kernel<BN><<<grid, gemm::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);

@@ -8,6 +8,7 @@ struct LinearArgs {
   const float *bias, *row_scale;
   void *y;
   int64_t M, rows_per_sample, ldy, ldr;
+  int64_t res_period;   // residual row = m % res_period (0: residual has M rows)
   int N, K, epilogue;
 };
 

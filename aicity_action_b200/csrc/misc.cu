@@ -93,6 +93,38 @@ __global__ void preprocess_u8_kernel(const uint8_t *__restrict__ in, T *__restri
   }
 }
 
+
+// im2col for Conv3d: one thread per (output token, c, a, b) segment of kw contiguous taps.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col3d_kernel(const T *__restrict__ x, T *__restrict__ out, int B, int C, int Ti,
+                                                       int H, int W, int kt, int kh, int kw, int st, int sh, int sw,
+                                                       int pt, int ph, int pw, int To, int Ho, int Wo, int Kp) {
+  const int segs = C * kt * kh;                 // real segments per row
+  const int segs_p = (Kp + kw - 1) / kw;        // incl. the zero-pad tail
+  const int64_t total = (int64_t)B * To * Ho * Wo * segs_p;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int seg = (int)(i % segs_p);
+    const int64_t m = i / segs_p;
+    T *dst = out + m * Kp + seg * kw;
+    const int nvalid = min(kw, Kp - seg * kw);
+    if (seg >= segs) {
+      for (int d = 0; d < nvalid; ++d) dst[d] = from_f32<T>(0.f);
+      continue;
+    }
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), to = (int)((m / ((int64_t)Wo * Ho)) % To);
+    const int b = (int)(m / ((int64_t)Wo * Ho * To));
+    const int bq = seg % kh, a = (seg / kh) % kt, c = seg / (kh * kt);
+    const int t = to * st - pt + a, h = ho * sh - ph + bq, w0 = wo * sw - pw;
+    const bool row_ok = t >= 0 && t < Ti && h >= 0 && h < H;
+    const T *src = x + ((((int64_t)b * C + c) * Ti + (row_ok ? t : 0)) * H + (row_ok ? h : 0)) * W;
+    for (int d = 0; d < nvalid; ++d) {
+      const int w = w0 + d;
+      dst[d] = (row_ok && w >= 0 && w < W) ? src[w] : from_f32<T>(0.f);
+    }
+  }
+}
+
 }  // namespace mvit
 
 extern "C" int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
@@ -163,5 +195,28 @@ extern "C" int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, 
     preprocess_u8_kernel<bf16><<<blocks, threads, 0, st>>>(frames, static_cast<bf16 *>(clip), ppc, total, mean, stdv);
   else MVIT_REQUIRE(false, "preprocess: unknown dtype");
   MVIT_LAUNCH_OK("preprocess_u8");
+  return 0;
+}
+
+extern "C" int mvit_im2col3d_fwd(const void *clip, void *patches, int B, int C, int T, int H, int W, int kt, int kh,
+                                 int kw, int st, int sh, int sw, int pt, int ph, int pw, int Kp, int dtype,
+                                 void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(clip && patches, "im2col3d: null pointer");
+  MVIT_REQUIRE(B >= 0 && C > 0 && T > 0 && H > 0 && W > 0 && kt > 0 && kh > 0 && kw > 0 && st > 0 && sh > 0 && sw > 0,
+               "im2col3d: bad shape");
+  MVIT_REQUIRE(Kp >= C * kt * kh * kw, "im2col3d: Kp smaller than C*kt*kh*kw");
+  const int To = (T + 2 * pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  MVIT_REQUIRE(To > 0 && Ho > 0 && Wo > 0, "im2col3d: empty output");
+  if (B == 0) return 0;
+  const int64_t total = (int64_t)B * To * Ho * Wo * ((Kp + kw - 1) / kw);
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 64);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MVIT_F32)
+    im2col3d_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float *>(clip), static_cast<float *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
+  else if (dtype == MVIT_BF16)
+    im2col3d_kernel<bf16><<<blocks, 256, 0, s>>>(static_cast<const bf16 *>(clip), static_cast<bf16 *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
+  else MVIT_REQUIRE(false, "im2col3d: unknown dtype");
+  MVIT_LAUNCH_OK("im2col3d");
   return 0;
 }

@@ -45,22 +45,37 @@ class PatchEmbed(nn.Module):
         self.proj = conv(dim_in, dim_out, kernel_size=kernel, stride=stride, padding=padding)
         self.conv_2d = conv_2d
 
-    def forward(self, x, dtype=None):
+    def _gemm_weight(self, dtype):
+        """Conv weight as a [Cout, Kp] GEMM operand (Kp = C*kt*kh*kw rounded up to 64, zero padded), cached."""
+        w = self.proj.weight
+        key = (dtype, w._version, w.device, w.data_ptr())
+        slot = getattr(self, "_b200_w", None)
+        if slot is None or slot[0] != key:
+            k = w[0].numel()
+            kp = (k + 63) // 64 * 64
+            wp = torch.zeros((w.shape[0], kp), dtype=dtype, device=w.device)
+            wp[:, :k] = w.detach().reshape(w.shape[0], k).to(dtype)
+            slot = (key, wp)
+            self._b200_w = slot
+        return slot[1]
+
+    def forward(self, x, dtype=None, pos=None, pos_period=0):
+        """x: [B, C, T, H, W] (or [B, C, H, W] for conv_2d) -> tokens [B, L, Cout].
+        The convolution runs as im2col + one GEMM (tensor cores for bf16); `pos` ([pos_period, Cout] table
+        in the activation dtype) is added in the GEMM epilogue together with the bias."""
         if not x.is_cuda:
             raise ops._lib.MvitLibraryError("aicity_action_b200 runs on CUDA tensors only (no CPU fallback)")
         dtype = dtype or x.dtype
-        w = cached_weight(self.proj.weight, dtype)
-        b = cached_weight(self.proj.bias, dtype)
+        t3 = lambda v: [1] + list(v) if self.conv_2d else list(v)
         if self.conv_2d:
-            y = torch.nn.functional.conv2d(x.to(dtype).contiguous(memory_format=torch.channels_last), w, b,
-                                           self.proj.stride, self.proj.padding)
-            return y.permute(0, 2, 3, 1).flatten(1, 2)
-        # fp32 must be true fp32 (cuDNN would otherwise use TF32 and break the 1e-4 parity bound)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            y = torch.nn.functional.conv3d(x.to(dtype).contiguous(memory_format=torch.channels_last_3d),
-                                           w.contiguous(memory_format=torch.channels_last_3d), b,
-                                           self.proj.stride, self.proj.padding)
-        return y.permute(0, 2, 3, 4, 1).flatten(1, 3)      # [B, T'H'W', C]; a view when y is NDHWC
+            x = x.unsqueeze(2)
+        kernel, stride, padding = t3(self.proj.kernel_size), t3(self.proj.stride), t3(self.proj.padding)
+        if self.conv_2d:
+            padding[0] = 0
+        w = self._gemm_weight(dtype)
+        patches, _ = ops.im2col3d(x.to(dtype), kernel, stride, padding, w.shape[1])
+        y = ops.linear(patches, w, self.proj.bias, residual=pos, residual_row_period=pos_period if pos is not None else 0)
+        return y.view(x.shape[0], -1, w.shape[0])
 
 
 class TransformerBasicHead(nn.Module):
@@ -262,13 +277,27 @@ class MViT(nn.Module):
             return pos
         return self.pos_embed
 
+    def _pos_tokens(self, dtype):
+        """[N, C] separable positional-embedding table in the activation dtype (cached per parameter version)."""
+        ps, pt = self.pos_embed_spatial, self.pos_embed_temporal
+        key = (dtype, ps._version, pt._version, ps.device, ps.data_ptr(), pt.data_ptr())
+        slot = getattr(self, "_b200_pos", None)
+        if slot is None or slot[0] != key:
+            T, H, W = self.patch_dims
+            tab = (ps.detach().repeat(1, T, 1) + torch.repeat_interleave(pt.detach(), H * W, dim=1))[0]
+            slot = (key, tab.to(dtype).contiguous())
+            self._b200_pos = slot
+        return slot[1]
+
     def forward_features(self, x, dtype):
-        tokens = self.patch_embed(x, dtype)                      # [B, N, C]
         T, H, W = self.patch_dims
-        B = tokens.shape[0]
         if self.sep_pos_embed and not self.cls_embed_on:
-            x = ops.pos_embed_add(tokens, self.pos_embed_spatial, self.pos_embed_temporal, T, dtype)
+            # bias + positional embedding ride in the patch-embed GEMM epilogue
+            pos = self._pos_tokens(dtype)
+            x = self.patch_embed(x, dtype, pos=pos, pos_period=pos.shape[0])
         else:
+            tokens = self.patch_embed(x, dtype)                  # [B, N, C]
+            B = tokens.shape[0]
             if self.cls_embed_on:
                 tokens = torch.cat((self.cls_token.to(tokens.dtype).expand(B, -1, -1), tokens), dim=1)
             pos = self._pos_table(dtype).detach()

@@ -98,8 +98,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
            residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
-           gelu: bool = False, out: Optional[torch.Tensor] = None, impl: int = IMPL_AUTO) -> torch.Tensor:
-    """y = epi(x·wᵀ + bias)·row_scale + residual ; x [..., K], w [N, K] (same dtype as x)."""
+           gelu: bool = False, out: Optional[torch.Tensor] = None, impl: int = IMPL_AUTO,
+           residual_row_period: int = 0) -> torch.Tensor:
+    """y = epi(x·wᵀ + bias)·row_scale + residual ; x [..., K], w [N, K] (same dtype as x).
+    residual_row_period = P > 0: `residual` is a [P, N] table and row m adds row m % P."""
     global launch_count
     _need_cuda(x, w, bias, residual, row_scale)
     x = x.contiguous()
@@ -111,7 +113,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     assert y.is_contiguous() and y.numel() == M * N
     if residual is not None:
         residual = residual.contiguous()
-        assert residual.numel() == M * N and residual.dtype == x.dtype
+        assert residual.numel() == (residual_row_period or M) * N and residual.dtype == x.dtype
     rows_per_sample = 0
     if row_scale is not None:
         row_scale = _f32c(row_scale).reshape(-1)
@@ -120,7 +122,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     bias = _f32c(bias)
     with _Timed("linear", 2.0 * M * N * K):
         check(_lib.load().mvit_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(row_scale),
-                                          rows_per_sample, _ptr(y), M, N, K, N, N,
+                                          rows_per_sample, _ptr(y), M, N, K, N, N, int(residual_row_period),
                                           EPI_GELU if gelu else EPI_NONE, _dt(x), impl, _stream()),
               "mvit_linear_fwd")
     launch_count += 1
@@ -252,3 +254,18 @@ def preprocess_u8(frames: torch.Tensor, dtype: torch.dtype, mean: float = 0.45, 
                                              _DT[dtype], _stream()), "mvit_preprocess_u8_fwd")
     launch_count += 1
     return out
+
+
+def im2col3d(clip: torch.Tensor, kernel: Sequence[int], stride: Sequence[int], padding: Sequence[int], Kp: int):
+    """clip [B, C, T, H, W] -> patch matrix [B*To*Ho*Wo, Kp] (zero padded), see mvit_im2col3d_fwd."""
+    global launch_count
+    _need_cuda(clip)
+    clip = clip.contiguous()
+    B, Cc, T, H, W = clip.shape
+    To, Ho, Wo = [(n + 2 * p - k) // s + 1 for n, k, s, p in zip((T, H, W), kernel, stride, padding)]
+    out = torch.empty((B * To * Ho * Wo, Kp), dtype=clip.dtype, device=clip.device)
+    with _Timed("im2col", float(out.numel() + clip.numel()) * clip.element_size()):
+        check(_lib.load().mvit_im2col3d_fwd(_ptr(clip), _ptr(out), B, Cc, T, H, W, *kernel, *stride, *padding, Kp,
+                                            _dt(clip), _stream()), "mvit_im2col3d_fwd")
+    launch_count += 1
+    return out, [To, Ho, Wo]

@@ -69,10 +69,24 @@ int mvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, voi
  *   bias, residual, row_scale may be NULL.  row_scale[b] multiplies (x·wᵀ+bias) for rows
  *   [b*rows_per_sample, (b+1)*rows_per_sample) BEFORE the residual is added (common.py:46-59).
  *   ldy / ldr: leading dimensions (elements) of y and residual (>= N).
+ *   residual_row_period: 0 = residual has M rows; P > 0 = residual has P rows and row m reads row m % P
+ *   (the positional-embedding table broadcast over the batch, video_model_builder.py:1206-1223).
  */
 int mvit_linear_fwd(const void *x, const void *w, const float *bias, const void *residual,
                     const float *row_scale, int64_t rows_per_sample, void *y, int64_t M, int N,
-                    int K, int64_t ldy, int64_t ldr, int epilogue, int dtype, int impl, void *stream);
+                    int K, int64_t ldy, int64_t ldr, int64_t residual_row_period, int epilogue,
+                    int dtype, int impl, void *stream);
+
+/*
+ * im2col for the patch-embedding Conv3d (stem_helper.py:308-338): clip [B, C, T, H, W] (channels-first,
+ * as the reference feeds it) -> patch matrix [B*To*Ho*Wo, Kp] with column k = ((c*kt + a)*kh + b)*kw + d
+ * (the natural flattening of the Conv3d weight [Cout, C, kt, kh, kw]); zero padding outside the clip and
+ * in columns [C*kt*kh*kw, Kp).  The convolution itself is then mvit_linear_fwd on tensor cores with the
+ * bias and the positional embedding fused in its epilogue.
+ */
+int mvit_im2col3d_fwd(const void *clip, void *patches, int B, int C, int T, int H, int W, int kt, int kh,
+                      int kw, int st, int sh, int sw, int pt, int ph, int pw, int Kp, int dtype,
+                      void *stream);
 
 /*
  * attention_pool (attention.py:12-83) fused with its LayerNorm (attention.py:66-67).

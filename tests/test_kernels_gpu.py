@@ -167,3 +167,23 @@ def test_preprocess_u8_bit_exact_fp32():
     assert np.array_equal(got, np.ascontiguousarray(ref))
     got16 = ops.preprocess_u8(fr.cuda(), torch.bfloat16).float().cpu()
     assert torch.equal(got16, torch.from_numpy(np.ascontiguousarray(ref)).bfloat16().float())
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_patch_embed_im2col_gemm(dtype):
+    """im2col + GEMM (+bias, + positional table broadcast over the batch) == Conv3d + pos-embed add."""
+    B, T, S = 2, 8, 32
+    x = rounded(synth_input(6, "clip", (B, 3, T, S, S)), dtype)
+    w = rounded(synth_input(6, "pw", (96, 3, 3, 7, 7)) / 21.0, dtype)
+    bias = synth_input(6, "pb", (96,)) * 0.1
+    ref = F.conv3d(x, w, bias, stride=(2, 4, 4), padding=(1, 3, 3)).flatten(2).transpose(1, 2)   # [B, N, 96]
+    N = ref.shape[1]
+    pos = rounded(synth_input(6, "pos", (N, 96)) * 0.1, dtype)
+    ref = ref + pos
+    patches, thw = ops.im2col3d(dev(x, dtype), [3, 7, 7], [2, 4, 4], [1, 3, 3], 448)
+    assert thw == [4, 8, 8] and patches.shape == (B * N, 448)
+    wp = torch.zeros(96, 448)
+    wp[:, :441] = w.reshape(96, 441)
+    for impl in _impls(dtype):
+        got = ops.linear(patches, dev(wp, dtype), dev(bias), residual=dev(pos, dtype), residual_row_period=N, impl=impl)
+        assert rel_inf(got.view(B, N, 96), ref) < TOL[dtype], impl
