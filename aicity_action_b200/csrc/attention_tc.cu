@@ -37,6 +37,28 @@ __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, no ran
   return y;
 }
 
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], rel. error 7.5e-5, far below the
+// bf16 resolution of P): x = n + f, 2^x = 2^f * 2^n with n folded into the exponent bits.  Used for a quarter of
+// the score elements so the MUFU pipe stops being the attention bottleneck (SURVEY.md §7 "hard parts").
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 xc = make_float2(fmaxf(x.x, -120.f), fmaxf(x.y, -120.f));
+  const float2 t = __fadd2_rn(xc, make_float2(12582912.f, 12582912.f));        // round-to-nearest integer in low bits
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), xc);                 // [-0.5, 0.5]
+  float2 r = __ffma2_rn(f, make_float2(0.055171817541122437f, 0.055171817541122437f),
+                        make_float2(0.2426111400127411f, 0.2426111400127411f));
+  r = __ffma2_rn(r, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  r = __ffma2_rn(r, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  return make_float2(__int_as_float(__float_as_int(r.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(r.y) + (__float_as_int(t.y) << 23)));
+}
+
+// fp32 pair -> packed bf16x2 with round-half-up on the integer pipe (F2FP shares the MUFU pipe on sm_100 and was
+// costing as much as the exponentials themselves; values here are finite and >= 0)
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+
 struct Params {
   const bf16 *q;
   bf16 *out;
@@ -235,10 +257,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int e = 0; e < 32; ++e) {
             const int c = hlf * 2 + (e >> 4), idx = (e & 15) * 2;
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][idx]), __uint_as_float(s[c][idx + 1])), c2, nm2);
-            const float2 pe = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
             psum2 = __fadd2_rn(psum2, pe);
-            __nv_bfloat162 h = __floats2bfloat162_rn(pe.x, pe.y);
-            pk[e] = *reinterpret_cast<uint32_t *>(&h);
+            pk[e] = pack_bf16x2_alu(pe.x, pe.y);
           }
           tmem_st32(tS + hlf * 32, pk);
         }

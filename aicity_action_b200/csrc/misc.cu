@@ -94,33 +94,53 @@ __global__ void preprocess_u8_kernel(const uint8_t *__restrict__ in, T *__restri
 }
 
 
-// im2col for Conv3d: one thread per (output token, c, a, b) segment of kw contiguous taps.
+// im2col for Conv3d.  One thread produces 8 consecutive columns of one patch row (a single 16-byte store for
+// bf16, two for fp32).  Column k -> (c, a, b, d) is decoded once per CTA into a shared-memory table holding the
+// element offset inside a [C, T, H, W] clip and the (a, b, d) tap coordinates for the border test.
 template <typename T>
 __global__ void __launch_bounds__(256) im2col3d_kernel(const T *__restrict__ x, T *__restrict__ out, int B, int C, int Ti,
                                                        int H, int W, int kt, int kh, int kw, int st, int sh, int sw,
                                                        int pt, int ph, int pw, int To, int Ho, int Wo, int Kp) {
-  const int segs = C * kt * kh;                 // real segments per row
-  const int segs_p = (Kp + kw - 1) / kw;        // incl. the zero-pad tail
-  const int64_t total = (int64_t)B * To * Ho * Wo * segs_p;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int seg = (int)(i % segs_p);
-    const int64_t m = i / segs_p;
-    T *dst = out + m * Kp + seg * kw;
-    const int nvalid = min(kw, Kp - seg * kw);
-    if (seg >= segs) {
-      for (int d = 0; d < nvalid; ++d) dst[d] = from_f32<T>(0.f);
-      continue;
+  extern __shared__ int2 lut[];                 // [Kp]: .x = element offset (or -1 for padding columns), .y = a | b<<8 | d<<16
+  const int kreal = C * kt * kh * kw;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    if (k < kreal) {
+      const int d = k % kw, bq = (k / kw) % kh, a = (k / (kw * kh)) % kt, c = k / (kw * kh * kt);
+      lut[k] = make_int2(((c * Ti + a) * H + bq) * W + d, a | (bq << 8) | (d << 16));
+    } else {
+      lut[k] = make_int2(-1, 0);
     }
+  }
+  __syncthreads();
+  const int vecs = Kp / 8;
+  const int64_t total = (int64_t)B * To * Ho * Wo * vecs;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t clip_elems = (int64_t)C * Ti * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = (int)(i % vecs);
+    const int64_t m = i / vecs;
     const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), to = (int)((m / ((int64_t)Wo * Ho)) % To);
     const int b = (int)(m / ((int64_t)Wo * Ho * To));
-    const int bq = seg % kh, a = (seg / kh) % kt, c = seg / (kh * kt);
-    const int t = to * st - pt + a, h = ho * sh - ph + bq, w0 = wo * sw - pw;
-    const bool row_ok = t >= 0 && t < Ti && h >= 0 && h < H;
-    const T *src = x + ((((int64_t)b * C + c) * Ti + (row_ok ? t : 0)) * H + (row_ok ? h : 0)) * W;
-    for (int d = 0; d < nvalid; ++d) {
-      const int w = w0 + d;
-      dst[d] = (row_ok && w >= 0 && w < W) ? src[w] : from_f32<T>(0.f);
+    const int t0 = to * st - pt, h0 = ho * sh - ph, w0 = wo * sw - pw;
+    const T *base = x + b * clip_elems + ((int64_t)t0 * H + h0) * W + w0;     // may point before the clip: only
+    const bool inside = t0 >= 0 && t0 + kt <= Ti && h0 >= 0 && h0 + kh <= H && w0 >= 0 && w0 + kw <= W;   // offset it
+    T vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int2 l = lut[v * 8 + e];
+      bool ok = l.x >= 0;
+      if (!inside && ok) {
+        const int t = t0 + (l.y & 0xff), h = h0 + ((l.y >> 8) & 0xff), w = w0 + (l.y >> 16);
+        ok = t >= 0 && t < Ti && h >= 0 && h < H && w >= 0 && w < W;
+      }
+      vals[e] = ok ? base[l.x] : from_f32<T>(0.f);
+    }
+    T *dst = out + m * Kp + v * 8;
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(vals);
+    } else {
+      *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(vals);
+      *reinterpret_cast<uint4 *>(dst + 4) = *reinterpret_cast<const uint4 *>(vals + 4);
     }
   }
 }
@@ -205,17 +225,20 @@ extern "C" int mvit_im2col3d_fwd(const void *clip, void *patches, int B, int C, 
   MVIT_REQUIRE(clip && patches, "im2col3d: null pointer");
   MVIT_REQUIRE(B >= 0 && C > 0 && T > 0 && H > 0 && W > 0 && kt > 0 && kh > 0 && kw > 0 && st > 0 && sh > 0 && sw > 0,
                "im2col3d: bad shape");
-  MVIT_REQUIRE(Kp >= C * kt * kh * kw, "im2col3d: Kp smaller than C*kt*kh*kw");
+  MVIT_REQUIRE(Kp >= C * kt * kh * kw && Kp % 8 == 0, "im2col3d: Kp must be a multiple of 8 and >= C*kt*kh*kw");
+  MVIT_REQUIRE((reinterpret_cast<uintptr_t>(patches) & 15) == 0, "im2col3d: output must be 16-byte aligned");
+  MVIT_REQUIRE(kt < 256 && kh < 256 && kw < 256 && Kp <= 4096, "im2col3d: kernel too large");
   const int To = (T + 2 * pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
   MVIT_REQUIRE(To > 0 && Ho > 0 && Wo > 0, "im2col3d: empty output");
   if (B == 0) return 0;
-  const int64_t total = (int64_t)B * To * Ho * Wo * ((Kp + kw - 1) / kw);
-  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 64);
+  const int64_t total = (int64_t)B * To * Ho * Wo * (Kp / 8);
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  const size_t smem = (size_t)Kp * sizeof(int2);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MVIT_F32)
-    im2col3d_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float *>(clip), static_cast<float *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
+    im2col3d_kernel<float><<<blocks, 256, smem, s>>>(static_cast<const float *>(clip), static_cast<float *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
   else if (dtype == MVIT_BF16)
-    im2col3d_kernel<bf16><<<blocks, 256, 0, s>>>(static_cast<const bf16 *>(clip), static_cast<bf16 *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
+    im2col3d_kernel<bf16><<<blocks, 256, smem, s>>>(static_cast<const bf16 *>(clip), static_cast<bf16 *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
   else MVIT_REQUIRE(false, "im2col3d: unknown dtype");
   MVIT_LAUNCH_OK("im2col3d");
   return 0;
