@@ -100,7 +100,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], two ? 2 : 1);   // one tcgen05.commit per active query tile
+      mbar_init(&kv_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -139,55 +139,57 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(vdst + c * kChunkBytes, &tmap_v, &v_full[s], c * kChunkCols, j * BKV, bh);
       }
-    } else if ((warp == 1 || warp == 3) && lane == 0) {
-      // -------------------------------------------------------------- MMA issuers: warp 1 drives query tile 0,
-      // warp 3 query tile 1.  Two independent issue streams: a tile's chain QK(j) -> softmax -> PV(j) -> QK(j+1)
-      // never waits behind the other tile's softmax; the tensor pipe interleaves whatever is ready.
-      const int i = warp == 1 ? 0 : 1;
-      if (i == 0 || two) {
-        constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
-        constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // A = P (TMEM),    B = V (MN-major)
-        const uint32_t sq = smem_u32(sQ) + i * kTileBytes, skv = smem_u32(sKV);
-        const uint32_t tS_i = tmem_base + kColS + i * BKV, tO_i = tmem_base + kColO + i * D;
-        auto issue_qk = [&](int s) {
-          const uint32_t b0 = skv + s * 2 * kTileBytes;
+    } else if (warp == 1 && lane == 0) {
+      // -------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // A = P (TMEM),    B = V (MN-major)
+      const uint32_t sq = smem_u32(sQ), skv = smem_u32(sKV);
+      auto issue_qk = [&](int i, int s) {
+        const uint32_t a0 = sq + i * kTileBytes, b0 = skv + s * 2 * kTileBytes;
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k >> 1) * kChunkBytes + (k & 1) * 32;
-            umma_ss(tS_i, make_smem_desc(sq + off, 16, 512, SWZ_64B), make_smem_desc(b0 + off, 16, 512, SWZ_64B),
-                    idesc_qk, k != 0);
-          }
-          umma_commit(&s_full[i]);
-        };
-        auto issue_pv = [&](int s, bool accumulate) {
-          const uint32_t v0 = skv + s * 2 * kTileBytes + kTileBytes;
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            // V tile: [128 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
-            umma_ts(tO_i, tS_i + k * 8, make_smem_desc(v0 + k * 16 * 64, kChunkBytes, 512, SWZ_64B), idesc_pv,
-                    (accumulate || k != 0));
-          }
-          umma_commit(&o_done[i]);
-        };
-        mbar_wait(q_full, 0);
-        mbar_wait(&k_full[0], 0);
-        tc_fence_after();
-        issue_qk(0);
-        for (int j = 0; j < nkv; ++j) {
-          const int s = j % kStages;
-          const uint32_t ph = (j / kStages) & 1;
-          mbar_wait(&v_full[s], ph);
-          mbar_wait(&p_ready[i], j & 1);               // softmax wrote P_i(j) (and rescaled O_i if needed)
-          tc_fence_after();
-          issue_pv(s, j > 0);
-          umma_commit(&kv_empty[s]);                   // this tile is done with K(j)/V(j) once PV completes
-          if (j + 1 < nkv) {
-            const int s1 = (j + 1) % kStages;
-            mbar_wait(&k_full[s1], ((j + 1) / kStages) & 1);
-            tc_fence_after();
-            issue_qk(s1);                              // in-order after PV_i(j): may overwrite S_i / P_i(j)
-          }
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 1) * kChunkBytes + (k & 1) * 32;
+          umma_ss(tmem_base + kColS + i * BKV, make_smem_desc(a0 + off, 16, 512, SWZ_64B),
+                  make_smem_desc(b0 + off, 16, 512, SWZ_64B), idesc_qk, k != 0);
         }
+        umma_commit(&s_full[i]);
+      };
+      auto issue_pv = [&](int i, int s, bool accumulate) {
+        const uint32_t v0 = skv + s * 2 * kTileBytes + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // V tile: [128 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
+          umma_ts(tmem_base + kColO + i * D, tmem_base + kColS + i * BKV + k * 8,
+                  make_smem_desc(v0 + k * 16 * 64, kChunkBytes, 512, SWZ_64B), idesc_pv, (accumulate || k != 0));
+        }
+        umma_commit(&o_done[i]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        mbar_wait(&k_full[s], ph);
+        tc_fence_after();
+        issue_qk(0, s);
+        if (two && j > 0) {
+          mbar_wait(&p_ready[1], (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, (j - 1) % kStages, j - 1 > 0);
+          umma_commit(&kv_empty[(j - 1) % kStages]);
+        }
+        if (two) issue_qk(1, s);
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(&p_ready[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, s, j > 0);
+        if (!two) umma_commit(&kv_empty[s]);
+      }
+      if (two) {
+        mbar_wait(&p_ready[1], (nkv - 1) & 1);
+        tc_fence_after();
+        issue_pv(1, (nkv - 1) % kStages, nkv - 1 > 0);
+        umma_commit(&kv_empty[(nkv - 1) % kStages]);
       }
     }
   } else {
