@@ -218,15 +218,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int e = 0; e < 32; ++e)
               if (c * 32 + e >= valid) s[c][e] = 0xff800000u;   // -inf
         }
-        float mx = -INFINITY;
+        if (j == 0) {                                 // first tile: the reference maximum is this tile's own
+          float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[c][e]));
-        const float m_tile = mx * p.scale_log2;
-        if (j == 0) {
-          m_used = m_tile;
-        } else {
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[c][e]));
+          m_used = mx * p.scale_log2;
+        }
+        // One pass: P = exp2(s*scale_log2 - m_used) against the running (possibly stale) maximum while the tile
+        // maximum is reduced on the side; max / exp / sum / pack of different elements are independent, so the
+        // ALU, FMA and MUFU pipes overlap.  If a row maximum grew by more than 2^8 the pass is repeated after
+        // rescaling O (rare: first tiles only).
+        const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+        float psum = 0.f;
+        auto softmax_pass = [&](float m_ref) -> float {
+          const float2 nm2 = make_float2(-m_ref, -m_ref);
+          float2 psum2 = make_float2(0.f, 0.f);
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int c = hlf * 2 + (e >> 4), idx = (e & 15) * 2;
+              const float s0 = __uint_as_float(s[c][idx]), s1 = __uint_as_float(s[c][idx + 1]);
+              if (e & 1) mx1 = fmaxf(mx1, fmaxf(s0, s1));
+              else mx0 = fmaxf(mx0, fmaxf(s0, s1));
+              const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
+              const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+              psum2 = __fadd2_rn(psum2, pe);
+              pk[e] = pack_bf16x2_alu(pe.x, pe.y);
+            }
+            tmem_st32(tS + hlf * 32, pk);             // P (bf16) over S columns [0, 64); S itself stays in registers
+          }
+          psum = psum2.x + psum2.y;
+          return fmaxf(mx0, mx1) * p.scale_log2;
+        };
+        const float m_tile = softmax_pass(m_used);
+        if (j > 0) {
           const float m_new = fmaxf(m_used, m_tile);
           const bool need = (m_new - m_used) > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
@@ -245,25 +275,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               tmem_st32(tO + c * 32, o);
             }
             tmem_st_wait();
+            softmax_pass(m_used);                     // recompute P against the new maximum
           }
         }
-        // P = exp2(s*scale_log2 - m_used), bf16-packed in place over S columns [0, 64)
-        const float2 c2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_used, -m_used);
-        float2 psum2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int c = hlf * 2 + (e >> 4), idx = (e & 15) * 2;
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][idx]), __uint_as_float(s[c][idx + 1])), c2, nm2);
-            const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-            psum2 = __fadd2_rn(psum2, pe);
-            pk[e] = pack_bf16x2_alu(pe.x, pe.y);
-          }
-          tmem_st32(tS + hlf * 32, pk);
-        }
-        const float psum = psum2.x + psum2.y;
         l_run += psum;
         tmem_st_wait();
         tc_fence_before();

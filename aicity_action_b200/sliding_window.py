@@ -1,0 +1,160 @@
+"""Sliding-window temporal localisation over long driver videos, sharded across the GPUs of one box.
+
+B200 form of scripts/run_action_classification_temporal_inf.py:75-130 + the window/frame logic of
+scripts/module_wrapper.py:215-253, 304-397 (reference file:line cited per function):
+
+  * window list and per-window frame indices are computed on the host exactly as the reference does
+    (integer loop; float32 `torch.linspace` + clamp + truncate) — bit-exact by construction;
+  * windows are dealt to ranks round-robin (window w -> rank w % R); every rank runs the replicated model
+    on batches of its own windows: uint8 frames go up over PCIe (1 byte/sample), normalisation happens on
+    the device (mvit_preprocess_u8_fwd), the forward is the tcgen05 path;
+  * per-window probabilities are exchanged with ONE collective per video — an all_gather of a padded
+    [ceil(n/R), 2 + classes] fp32/int64 pair over NCCL (NVLink/NVSwitch; gloo in CPU tests) — and put back in
+    window order, which equals the reference's `pred_list.sort(key=t0)` order (module_wrapper windows have
+    strictly increasing t0), so rank 0 writes byte-identical (t0, t1, scores) lists.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+# ----------------------------------------------------------------------------- host-side indexing
+def fps_adjusted_window(length: int, stride: int, video_fps: float, target_fps: float = 30.0) -> Tuple[int, int]:
+    """module_wrapper.py:215-232: windows are rescaled only when |video_fps - target_fps| > 2 (int() truncation)."""
+    if abs(video_fps - target_fps) > 2.0:
+        r = video_fps / target_fps
+        return int(r * length), int(r * stride)
+    return length, stride
+
+
+def window_list(num_frames: int, length: int = 64, stride: int = 16) -> List[Tuple[int, int]]:
+    """module_wrapper.py:246-253: (t0, t1) for t0 in range(0, num_frames, stride); t1 may pass the end."""
+    return [(t0, t0 + length) for t0 in range(0, num_frames, stride)]
+
+
+def frame_indices(t0: int, t1: int, num: int, num_frames: int) -> List[int]:
+    """module_wrapper.py:384-397: `num` points uniformly in [t0, t1] (endpoint inclusive, float32), clamped to
+    the video and truncated.  torch.linspace is called as the reference calls it, not re-derived."""
+    idx = torch.linspace(t0, t1, num)
+    return torch.clamp(idx, 0, num_frames - 1).long().numpy().tolist()
+
+
+def shard_windows(n_windows: int, rank: int, world: int) -> List[int]:
+    """Round-robin deal: window w belongs to rank w % world."""
+    return list(range(rank, n_windows, world))
+
+
+# ----------------------------------------------------------------------------- video sources
+class SyntheticVideo:
+    """Procedural stand-in for a decoded + resized video: frame f of video `seed` is a deterministic function of
+    (seed, f) only, so any rank can materialise any frame without I/O.  Frames are uint8 [S, S, 3] RGB — what the
+    reference holds after `cv2.resize(frame, (S, S))` (scripts/utils.py:207-211)."""
+
+    def __init__(self, seed: int, num_frames: int, size: int, fps: float = 30.0):
+        self.seed, self.num_frames, self.size, self.fps = seed, num_frames, size, fps
+        g = torch.Generator().manual_seed(seed)
+        self._base = torch.randint(0, 256, (size, size, 3), dtype=torch.uint8, generator=g)
+        self._ramp = torch.arange(size, dtype=torch.int32).view(size, 1, 1)
+
+    def __len__(self):
+        return self.num_frames
+
+    def frame(self, f: int) -> torch.Tensor:
+        # cheap, frame-dependent, deterministic: circular shift of a base texture plus a moving ramp
+        img = torch.roll(self._base, shifts=(f % self.size, (3 * f) % self.size), dims=(0, 1)).to(torch.int32)
+        return ((img + (self._ramp * (f % 7))) % 256).to(torch.uint8)
+
+    def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
+        return torch.stack([self.frame(int(i)) for i in idxs])      # [T, S, S, 3]
+
+
+# ----------------------------------------------------------------------------- the runner
+@dataclass
+class WindowPrediction:
+    t0: int
+    t1: int
+    scores: np.ndarray       # [num_classes] float32
+
+
+class SlidingWindowRunner:
+    """Runs the replicated classifier over one rank's share of the windows of each video and gathers scores.
+
+    `model` is anything with the reference inference contract `model([clip]) -> [B, classes]` on CUDA clips
+    (aicity_action_b200.mvit.MViT); `preprocess(frames_u8_device) -> clip` defaults to the on-device normalisation.
+    With `device=None` the runner only does the host-side logic (used by the gloo CPU tests with a stub model)."""
+
+    def __init__(self, model: Callable, num_frames: int = 16, sampling_rate: int = 4, proposal_stride: int = 16,
+                 batch_size: int = 8, dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
+                 rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None):
+        self.model, self.T, self.rate = model, num_frames, sampling_rate
+        self.length, self.stride = num_frames * sampling_rate, proposal_stride   # run_action...py:76
+        self.batch_size, self.dtype, self.device = batch_size, dtype, device
+        self.rank, self.world, self.group = rank, world, group
+        if preprocess is None and device is not None:
+            from . import ops
+            preprocess = lambda u8: ops.preprocess_u8(u8, dtype)
+        self.preprocess = preprocess
+
+    def windows_for(self, video) -> List[Tuple[int, int]]:
+        length, stride = fps_adjusted_window(self.length, self.stride, getattr(video, "fps", 30.0))
+        return window_list(len(video), length, stride)
+
+    @torch.no_grad()
+    def local_scores(self, video, windows: List[Tuple[int, int]]) -> Tuple[List[int], torch.Tensor]:
+        """Scores of this rank's windows: (window ids, [n_local, classes] float32 on CPU)."""
+        mine = shard_windows(len(windows), self.rank, self.world)
+        outs = []
+        for b0 in range(0, len(mine), self.batch_size):
+            ids = mine[b0:b0 + self.batch_size]
+            frames = torch.stack([video.get_batch(frame_indices(*windows[w], self.T, len(video))) for w in ids])
+            if self.device is not None:
+                frames = frames.pin_memory().to(self.device, non_blocking=True)
+            clip = self.preprocess(frames) if self.preprocess is not None else frames
+            outs.append(self.model([clip]).float().cpu())
+        scores = torch.cat(outs) if outs else torch.zeros((0, 0))
+        return mine, scores
+
+    def gather(self, n_windows: int, mine: List[int], scores: torch.Tensor, num_classes: int) -> Optional[torch.Tensor]:
+        """One all_gather per video of a padded [ceil(n/R), 1 + classes] block (window id, scores); returns the
+        [n_windows, classes] table in window order on every rank."""
+        if self.world == 1:
+            return scores
+        import torch.distributed as dist
+        per = (n_windows + self.world - 1) // self.world
+        block = torch.full((per, 1 + num_classes), -1.0, dtype=torch.float32)
+        if len(mine):
+            block[:len(mine), 0] = torch.tensor(mine, dtype=torch.float32)
+            block[:len(mine), 1:] = scores
+        dev = self.device if (self.device is not None and dist.get_backend(self.group) == "nccl") else torch.device("cpu")
+        block = block.to(dev)
+        out = [torch.empty_like(block) for _ in range(self.world)]
+        dist.all_gather(out, block, group=self.group)
+        table = torch.zeros((n_windows, num_classes), dtype=torch.float32)
+        for blk in out:
+            blk = blk.cpu()
+            ok = blk[:, 0] >= 0
+            table[blk[ok, 0].long()] = blk[ok, 1:]
+        return table
+
+    def run_video(self, video, num_classes: int) -> List[Tuple[int, int, np.ndarray]]:
+        """The reference's per-video result: [(t0, t1, scores[classes])] sorted by t0 (run_action...py:110-125)."""
+        windows = self.windows_for(video)
+        mine, scores = self.local_scores(video, windows)
+        table = self.gather(len(windows), mine, scores, num_classes)
+        preds = [(int(t0), int(t1), table[w].numpy()) for w, (t0, t1) in enumerate(windows)]
+        preds.sort(key=lambda x: x[0])
+        return preds
+
+    def run_and_save(self, video, video_name: str, out_dir: str, num_classes: int):
+        preds = self.run_video(video, num_classes)
+        if self.rank == 0:
+            os.makedirs(out_dir, exist_ok=True)
+            with open(os.path.join(out_dir, f"{video_name}.pkl"), "wb") as f:   # run_action...py:128-130
+                pickle.dump(preds, f)
+        return preds

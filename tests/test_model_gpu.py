@@ -107,3 +107,26 @@ def test_state_dict_roundtrip_and_deepcopy():
         p16 = a([x.bfloat16()])
         a.blocks[0].mlp.fc1.weight.mul_(0.5)
         assert not torch.equal(a([x.bfloat16()]), p16)
+
+
+def test_sliding_window_runner_matches_direct_inference():
+    """Windows of a synthetic video through the runner (uint8 upload, on-device normalise, bf16 forward) ==
+    the same clips pushed through the model directly; window order and (t0, t1) as the reference defines them."""
+    from aicity_action_b200 import ops
+    from aicity_action_b200 import sliding_window as SW
+    c = MODEL_CASES[0]
+    cfg = aicity_cfg(c["yaml"], tiny_cfg_overrides(c))
+    m = MViT(cfg).eval()
+    load_synth(m, c["seed"])
+    m = m.cuda()
+    video = SW.SyntheticVideo(seed=3, num_frames=200, size=cfg.DATA.TRAIN_CROP_SIZE)
+    runner = SW.SlidingWindowRunner(m, num_frames=cfg.DATA.NUM_FRAMES, sampling_rate=4, proposal_stride=16,
+                                    batch_size=4, device=torch.device("cuda"))
+    preds = runner.run_video(video, cfg.MODEL.NUM_CLASSES)
+    wins = SW.window_list(200, cfg.DATA.NUM_FRAMES * 4, 16)
+    assert [(a, b) for a, b, _ in preds] == wins
+    with torch.no_grad():
+        for w in (0, 5, len(wins) - 1):
+            fr = video.get_batch(SW.frame_indices(*wins[w], cfg.DATA.NUM_FRAMES, 200)).unsqueeze(0).cuda()
+            direct = m([ops.preprocess_u8(fr, torch.bfloat16)])[0].cpu().numpy()
+            assert abs(direct - preds[w][2]).max() < 2e-3

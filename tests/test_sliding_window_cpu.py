@@ -1,0 +1,90 @@
+"""CPU: window indexing / post-processing of the product against the reference-generated fixtures, and the
+world_size-2 sharded sliding-window path over gloo (stub classifier, so no GPU is involved)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aicity_action_b200 import postprocess as PP
+from aicity_action_b200 import sliding_window as SW
+
+
+def test_windows_and_indices_match_reference(golden, golden_index):
+    for key, n in golden_index["windows"].items():
+        _, nf, length, stride = key.split("_")
+        w = SW.window_list(int(nf), int(length), int(stride))
+        assert len(w) == n and np.array_equal(np.asarray(w), golden[key])
+        idx = [SW.frame_indices(t0, t1, 16, int(nf)) for t0, t1 in w]
+        assert np.array_equal(np.asarray(idx), golden[key + ".idx"])
+    assert SW.fps_adjusted_window(64, 16, 25.0) == (53, 13) and SW.fps_adjusted_window(64, 16, 29.97) == (64, 16)
+    assert len(SW.window_list(18000)) == 1125          # 10-min 30 fps video
+
+
+def test_chunks_and_aggregation_match_reference(golden, golden_index):
+    for ent in golden_index["chunks"]:
+        got = [(a, b, n, float(m)) for a, b, n, m, _ in PP.get_chunks(np.asarray(ent["scores"], np.float32), ent["thr"])]
+        assert got == [tuple(c) for c in ent["chunks"]]
+    wl = SW.window_list(300, 64, 16)
+    preds = [(t0, t1, golden["agg_in"][i]) for i, (t0, t1) in enumerate(wl)]
+    assert np.array_equal(PP.aggregate_predictions(preds, np.mean, 18), golden["agg_mean"])   # bit-exact
+    assert np.array_equal(PP.aggregate_predictions(preds, np.max, 18), golden["agg_max"])
+    assert PP.boundaries_to_seconds(75, 945) == (3.0, 31.0)     # 2.5 -> 2 and 31.5 -> 32: banker's rounding
+    assert PP.boundaries_to_seconds(45, 15) == (3.0, -1.0)
+
+
+class StubModel:
+    """Deterministic 'classifier' on uint8 frames: depends on every frame of the window."""
+
+    def __call__(self, x):
+        clip = x[0].float()                                   # [B, T, S, S, 3]
+        f = clip.mean(dim=(2, 3, 4))                          # [B, T]
+        logits = torch.stack([(f * (k + 1)).sin().sum(1) for k in range(18)], dim=1)
+        return logits.softmax(1)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    video = SW.SyntheticVideo(seed=5, num_frames=500, size=16)
+    r = SW.SlidingWindowRunner(StubModel(), batch_size=4, device=None, rank=rank, world=world, preprocess=None)
+    preds = r.run_video(video, 18)
+    q.put((rank, [(a, b, s.tolist()) for a, b, s in preds]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_windows_equal_single_rank_over_gloo():
+    video = SW.SyntheticVideo(seed=5, num_frames=500, size=16)
+    single = SW.SlidingWindowRunner(StubModel(), batch_size=4, device=None, preprocess=None).run_video(video, 18)
+    assert [p[0] for p in single] == list(range(0, 500, 16)) and len(single) == 32
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = [(a, b, s.tolist()) for a, b, s in single]
+    assert got[0] == ref and got[1] == ref            # byte-for-byte after the gather, on every rank
+
+
+def test_shard_is_a_partition():
+    for n, w in [(1125, 8), (7, 4), (0, 2), (33, 2)]:
+        parts = [SW.shard_windows(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
