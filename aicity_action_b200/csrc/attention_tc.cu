@@ -2,17 +2,19 @@
 //
 // Replaces attention.py:267-279 (bmm, *scale, softmax, bmm, transpose/reshape, +q): the [Lq, Lk] score
 // matrix lives only in tensor memory.  One CTA owns 256 query rows of one (batch, head) — two 128-row
-// tiles that share every K/V tile it streams — and runs five kinds of warps:
-//   warp 0      TMA producer: Q (once) and a 3-stage ring of K/V tiles, 64B-swizzled 32-column boxes;
-//   warp 1      MMA issuer (one lane): S_i = Q_i·Kᵀ (tcgen05.mma SS, M=128 N=128 K=16 x6) into TMEM and
-//               O_i += P_i·V (tcgen05.mma TS: P from TMEM, V MN-major from smem, N=96 K=16 x8), ordered
-//               QK0(j) PV1(j-1) QK1(j) PV0(j) so one tile's softmax overlaps the other tile's MMAs;
-//   warp 2      TMEM allocator (512 columns: S0 | S1 | O0 | O1);
-//   warps 4-7   softmax of tile 0, warps 8-11 softmax of tile 1: thread = query row (TMEM lane); reads
-//               S with tcgen05.ld, online softmax in the exp2 domain with lazy rescaling (O is only
-//               rescaled when a row maximum grows by more than 2^8), writes P (bf16) over S with
-//               tcgen05.st, and at the end normalises O, adds the pooled-q residual and stores
-//               [B, Lq, heads*96] directly (the head-merge transpose costs nothing).
+// query tiles ("streams") that share every 64-key K/V tile it loads — and runs five kinds of warps:
+//   warp 0      TMA producer: Q (once) and a 6-stage ring of K/V tiles (64 keys), 64B-swizzled 32-column boxes;
+//   warps 1, 3  MMA issuers, one lane each, one per stream: S = Q·Kᵀ (tcgen05.mma SS, M128 N64 K16 x6) into
+//               one of the stream's TWO score buffers in TMEM, and O += P·V (tcgen05.mma TS: P from TMEM,
+//               V MN-major from smem, N96 K16 x4).  Because S is double-buffered, QKᵀ of tile j+1 is issued
+//               before the softmax of tile j finishes: the softmax warps never wait for the tensor pipe.
+//   warp 2      TMEM allocator (S00 S01 S10 S11 | O0 O1 = 448 of 512 columns);
+//   warps 4-7 / 8-11  softmax of stream 0 / 1: thread = query row (TMEM lane); one pass per tile against the
+//               running (possibly stale) maximum — exp2 domain, 3/4 of the exponentials on MUFU and 1/4 on the
+//               FMA pipe (Cody-Waite + cubic), bf16 packing on the integer pipe, tile maximum reduced on the
+//               side; O is rescaled (and the pass repeated) only when a row maximum grew by more than 2^8.
+//               P (bf16) overwrites the first 32 columns of its score buffer with tcgen05.st.  At the end the
+//               warps normalise O, add the pooled-q residual and store [B, Lq, heads*96] directly.
 #include "attention.cuh"
 #include "tc_common.cuh"
 
@@ -20,16 +22,18 @@ namespace mvit {
 using namespace tc;
 
 namespace attn {
-constexpr int BQ = 128, BKV = 128, D = 96;
+constexpr int BQ = 128, BKV = 64, D = 96;
 constexpr int kChunkCols = 32, kChunks = 3;
-constexpr int kChunkBytes = 128 * kChunkCols * 2;   // 8 KB: 128 rows x 64 B, SWIZZLE_64B
-constexpr int kTileBytes = kChunks * kChunkBytes;   // 24 KB
-constexpr int kStages = 3;
+constexpr int kQChunkBytes = BQ * kChunkCols * 2;    // 8 KB: 128 rows x 64 B, SWIZZLE_64B
+constexpr int kQTileBytes = kChunks * kQChunkBytes;  // 24 KB
+constexpr int kKChunkBytes = BKV * kChunkCols * 2;   // 4 KB:  64 rows x 64 B
+constexpr int kKTileBytes = kChunks * kKChunkBytes;  // 12 KB
+constexpr int kStages = 6;
 constexpr int kThreads = 384;
-constexpr int kSmemBytes = 2 * kTileBytes + kStages * 2 * kTileBytes + 256 + 1024;
+constexpr int kSmemBytes = 2 * kQTileBytes + kStages * 2 * kKTileBytes + 512 + 1024;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256;          // S_i at 128*i, O_i at 256 + 96*i
-constexpr float kRescaleThreshold = 8.0f;           // log2 units
+constexpr uint32_t kColS = 0, kColO = 256;           // S[i][b] at 128*i + 64*b, O_i at 256 + 96*i
+constexpr float kRescaleThreshold = 8.0f;            // log2 units
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, no range fix-ups
   float y;
@@ -73,15 +77,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sQ = smem;                                  // [2][24 KB]
-  uint8_t *sKV = smem + 2 * kTileBytes;                // [stage][K 24 KB | V 24 KB]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * 2 * kTileBytes);
+  uint8_t *sKV = smem + 2 * kQTileBytes;               // [stage][K 12 KB | V 12 KB]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * 2 * kKTileBytes);
   uint64_t *q_full = bars;                 // 1
   uint64_t *k_full = bars + 1;             // kStages
   uint64_t *v_full = k_full + kStages;     // kStages
   uint64_t *kv_empty = v_full + kStages;   // kStages
-  uint64_t *s_full = kv_empty + kStages;   // 2
-  uint64_t *p_ready = s_full + 2;          // 2
-  uint64_t *o_done = p_ready + 2;          // 2
+  uint64_t *s_full = kv_empty + kStages;   // [stream][buffer]
+  uint64_t *p_ready = s_full + 4;          // [stream][buffer]
+  uint64_t *o_done = p_ready + 4;          // [stream]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,13 +104,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], two ? 2 : 1);   // one tcgen05.commit per active stream
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
-      mbar_init(&o_done[i], 1);
     }
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -119,101 +124,101 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {
       // -------------------------------------------------------------- TMA producer
       const int ntile = two ? 2 : 1;
-      mbar_arrive_expect_tx(q_full, ntile * kTileBytes);
+      mbar_arrive_expect_tx(q_full, ntile * kQTileBytes);
       for (int i = 0; i < ntile; ++i)
         for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(sQ + i * kTileBytes + c * kChunkBytes, &tmap_q, q_full, c * kChunkCols, q0 + i * BQ, bh);
+          tma_load_3d(sQ + i * kQTileBytes + c * kQChunkBytes, &tmap_q, q_full, c * kChunkCols, q0 + i * BQ, bh);
       for (int j = 0; j < nkv; ++j) {
         const int s = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t *kdst = sKV + s * 2 * kTileBytes, *vdst = kdst + kTileBytes;
-        mbar_arrive_expect_tx(&k_full[s], kTileBytes);
+        uint8_t *kdst = sKV + s * 2 * kKTileBytes, *vdst = kdst + kKTileBytes;
+        mbar_arrive_expect_tx(&k_full[s], kKTileBytes);
         for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(kdst + c * kChunkBytes, &tmap_k, &k_full[s], c * kChunkCols, j * BKV, bh);
-        mbar_arrive_expect_tx(&v_full[s], kTileBytes);
+          tma_load_3d(kdst + c * kKChunkBytes, &tmap_k, &k_full[s], c * kChunkCols, j * BKV, bh);
+        mbar_arrive_expect_tx(&v_full[s], kKTileBytes);
         for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(vdst + c * kChunkBytes, &tmap_v, &v_full[s], c * kChunkCols, j * BKV, bh);
+          tma_load_3d(vdst + c * kKChunkBytes, &tmap_v, &v_full[s], c * kChunkCols, j * BKV, bh);
       }
-    } else if (warp == 1 && lane == 0) {
-      // -------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // A = P (TMEM),    B = V (MN-major)
-      const uint32_t sq = smem_u32(sQ), skv = smem_u32(sKV);
-      auto issue_qk = [&](int i, int s) {
-        const uint32_t a0 = sq + i * kTileBytes, b0 = skv + s * 2 * kTileBytes;
+    } else if ((warp == 1 || warp == 3) && lane == 0) {
+      // -------------------------------------------------------------- MMA issuer of stream i
+      const int i = warp == 1 ? 0 : 1;
+      if (i == 0 || two) {
+        constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
+        constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // A = P (TMEM),    B = V (MN-major)
+        const uint32_t sq = smem_u32(sQ) + i * kQTileBytes, skv = smem_u32(sKV);
+        const uint32_t tS_i = tmem_base + kColS + i * 128, tO_i = tmem_base + kColO + i * D;
+        auto issue_qk = [&](int s, int b) {
+          const uint32_t k0 = skv + s * 2 * kKTileBytes;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 1) * kChunkBytes + (k & 1) * 32;
-          umma_ss(tmem_base + kColS + i * BKV, make_smem_desc(a0 + off, 16, 512, SWZ_64B),
-                  make_smem_desc(b0 + off, 16, 512, SWZ_64B), idesc_qk, k != 0);
-        }
-        umma_commit(&s_full[i]);
-      };
-      auto issue_pv = [&](int i, int s, bool accumulate) {
-        const uint32_t v0 = skv + s * 2 * kTileBytes + kTileBytes;
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t step = (k & 1) * 32;
+            umma_ss(tS_i + b * BKV, make_smem_desc(sq + (k >> 1) * kQChunkBytes + step, 16, 512, SWZ_64B),
+                    make_smem_desc(k0 + (k >> 1) * kKChunkBytes + step, 16, 512, SWZ_64B), idesc_qk, k != 0);
+          }
+          umma_commit(&s_full[i * 2 + b]);
+        };
+        auto issue_pv = [&](int s, int b, bool accumulate) {
+          const uint32_t v0 = skv + s * 2 * kKTileBytes + kKTileBytes;
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // V tile: [128 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
-          umma_ts(tmem_base + kColO + i * D, tmem_base + kColS + i * BKV + k * 8,
-                  make_smem_desc(v0 + k * 16 * 64, kChunkBytes, 512, SWZ_64B), idesc_pv, (accumulate || k != 0));
-        }
-        umma_commit(&o_done[i]);
-      };
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        mbar_wait(&k_full[s], ph);
-        tc_fence_after();
-        issue_qk(0, s);
-        if (two && j > 0) {
-          mbar_wait(&p_ready[1], (j - 1) & 1);
+          for (int k = 0; k < BKV / 16; ++k) {
+            // V tile: [64 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
+            umma_ts(tO_i, tS_i + b * BKV + k * 8, make_smem_desc(v0 + k * 16 * 64, kKChunkBytes, 512, SWZ_64B),
+                    idesc_pv, (accumulate || k != 0));
+          }
+          umma_commit(&o_done[i]);
+        };
+        mbar_wait(q_full, 0);
+        for (int jj = 0; jj < 2 && jj < nkv; ++jj) {  // fill both score buffers
+          mbar_wait(&k_full[jj % kStages], 0);
           tc_fence_after();
-          issue_pv(1, (j - 1) % kStages, j - 1 > 0);
-          umma_commit(&kv_empty[(j - 1) % kStages]);
+          issue_qk(jj % kStages, jj);
         }
-        if (two) issue_qk(1, s);
-        mbar_wait(&v_full[s], ph);
-        mbar_wait(&p_ready[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, s, j > 0);
-        if (!two) umma_commit(&kv_empty[s]);
-      }
-      if (two) {
-        mbar_wait(&p_ready[1], (nkv - 1) & 1);
-        tc_fence_after();
-        issue_pv(1, (nkv - 1) % kStages, nkv - 1 > 0);
-        umma_commit(&kv_empty[(nkv - 1) % kStages]);
+        for (int j = 0; j < nkv; ++j) {
+          const int s = j % kStages, b = j & 1;
+          mbar_wait(&v_full[s], (j / kStages) & 1);
+          mbar_wait(&p_ready[i * 2 + b], (j >> 1) & 1);   // softmax wrote P(j) (and rescaled O if needed)
+          tc_fence_after();
+          issue_pv(s, b, j > 0);
+          umma_commit(&kv_empty[s]);                   // this stream is done with K(j)/V(j) once PV(j) completes
+          if (j + 2 < nkv) {
+            const int s2 = (j + 2) % kStages;
+            mbar_wait(&k_full[s2], ((j + 2) / kStages) & 1);
+            tc_fence_after();
+            issue_qk(s2, b);                           // in-order after PV(j): may overwrite S/P of buffer b
+          }
+        }
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ---------------------------------------------------------------- softmax warpgroups
-    const int i = (warp - 4) >> 2;                    // which 128-row tile
+    const int i = (warp - 4) >> 2;                    // stream
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may touch
     if (i == 0 || two) {
       const int row = q0 + i * BQ + quarter * 32 + lane;
       const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-      const uint32_t tS = tmem_base + lane_base + kColS + i * BKV;
+      const uint32_t tS_i = tmem_base + lane_base + kColS + i * 128;
       const uint32_t tO = tmem_base + lane_base + kColO + i * D;
+      const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&s_full[i], j & 1);
+        const int b = j & 1;
+        const uint32_t tS = tS_i + b * BKV;
+        mbar_wait(&s_full[i * 2 + b], (j >> 1) & 1);
         tc_fence_after();
-        uint32_t s[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+        uint32_t s[2][32];
+        tmem_ld32(tS, s[0]);
+        tmem_ld32(tS + 32, s[1]);
         tmem_ld_wait();
         const int valid = p.Lk - j * BKV;             // >= 1
         if (valid < BKV) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (c * 32 + e >= valid) s[c][e] = 0xff800000u;   // -inf
@@ -221,37 +226,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (j == 0) {                                 // first tile: the reference maximum is this tile's own
           float mx = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[c][e]));
           m_used = mx * p.scale_log2;
         }
         // One pass: P = exp2(s*scale_log2 - m_used) against the running (possibly stale) maximum while the tile
         // maximum is reduced on the side; max / exp / sum / pack of different elements are independent, so the
-        // ALU, FMA and MUFU pipes overlap.  If a row maximum grew by more than 2^8 the pass is repeated after
-        // rescaling O (rare: first tiles only).
-        const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+        // ALU, FMA and MUFU pipes overlap.
         float psum = 0.f;
         auto softmax_pass = [&](float m_ref) -> float {
           const float2 nm2 = make_float2(-m_ref, -m_ref);
           float2 psum2 = make_float2(0.f, 0.f);
           float mx0 = -INFINITY, mx1 = -INFINITY;
+          uint32_t pk[32];
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t pk[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int c = hlf * 2 + (e >> 4), idx = (e & 15) * 2;
-              const float s0 = __uint_as_float(s[c][idx]), s1 = __uint_as_float(s[c][idx + 1]);
-              if (e & 1) mx1 = fmaxf(mx1, fmaxf(s0, s1));
-              else mx0 = fmaxf(mx0, fmaxf(s0, s1));
-              const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
-              const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-              psum2 = __fadd2_rn(psum2, pe);
-              pk[e] = pack_bf16x2_alu(pe.x, pe.y);
-            }
-            tmem_st32(tS + hlf * 32, pk);             // P (bf16) over S columns [0, 64); S itself stays in registers
+          for (int e = 0; e < 32; ++e) {
+            const int c = e >> 4, idx = (e & 15) * 2;
+            const float s0 = __uint_as_float(s[c][idx]), s1 = __uint_as_float(s[c][idx + 1]);
+            if (e & 1) mx1 = fmaxf(mx1, fmaxf(s0, s1));
+            else mx0 = fmaxf(mx0, fmaxf(s0, s1));
+            const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
+            const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            psum2 = __fadd2_rn(psum2, pe);
+            pk[e] = pack_bf16x2_alu(pe.x, pe.y);
           }
+          tmem_st32(tS, pk);                          // P (bf16) over the first 32 columns of this score buffer
           psum = psum2.x + psum2.y;
           return fmaxf(mx0, mx1) * p.scale_log2;
         };
@@ -259,7 +259,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (j > 0) {
           const float m_new = fmaxf(m_used, m_tile);
           const bool need = (m_new - m_used) > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
+          if (__any_sync(0xffffffffu, need)) {        // rare (first tiles): rescale O, then redo the pass
             mbar_wait(&o_done[i], (j - 1) & 1);       // PV(j-1) has landed in O
             tc_fence_after();
             const float alpha = ex2_approx(m_used - m_new);
@@ -275,13 +275,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               tmem_st32(tO + c * 32, o);
             }
             tmem_st_wait();
-            softmax_pass(m_used);                     // recompute P against the new maximum
+            softmax_pass(m_used);
           }
         }
         l_run += psum;
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[i]);
+        mbar_arrive(&p_ready[i * 2 + b]);
       }
       // ---- epilogue: O / l (+ q) -> out[b, row, head*96 + :]
       mbar_wait(&o_done[i], (nkv - 1) & 1);
@@ -336,16 +336,16 @@ bool attention_tc_supported(const AttnArgs &a, const char **why) {
 int attention_tc(const AttnArgs &a, cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   const int BH = a.B * a.heads;
-  auto enc = [&](CUtensorMap *m, const void *ptr, int L) {
+  auto enc = [&](CUtensorMap *m, const void *ptr, int L, int box_rows) {
     const uint64_t dims[3] = {(uint64_t)attn::D, (uint64_t)L, (uint64_t)BH};
     const uint64_t strides[2] = {(uint64_t)attn::D * 2, (uint64_t)L * attn::D * 2};
-    const uint32_t box[3] = {attn::kChunkCols, 128, 1};
+    const uint32_t box[3] = {attn::kChunkCols, (uint32_t)box_rows, 1};
     return encode_tmap_bf16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
   };
   int r;
-  if ((r = enc(&tq, a.q, a.Lq))) return r;
-  if ((r = enc(&tk, a.k, a.Lk))) return r;
-  if ((r = enc(&tv, a.v, a.Lk))) return r;
+  if ((r = enc(&tq, a.q, a.Lq, attn::BQ))) return r;
+  if ((r = enc(&tk, a.k, a.Lk, attn::BKV))) return r;
+  if ((r = enc(&tv, a.v, a.Lk, attn::BKV))) return r;
   static bool attr_done = false;
   if (!attr_done) {
     MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
