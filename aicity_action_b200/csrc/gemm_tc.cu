@@ -30,16 +30,21 @@ constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 384
 constexpr int kBoxCols = 32;               // output / residual boxes: 128 rows x 32 cols (64 B), SWIZZLE_64B
 constexpr int kBoxBytes = BM * kBoxCols * 2;
 
+// Two tile shapes:
+//   BN = 96  "narrow": memory-bound shapes (K <= 192): 4 operand stages, 4 in-place residual/output buffers;
+//   BN = 128 "wide":   compute-bound shapes (K >= 384): 5 operand stages of 32 KB keep ~4 k-blocks (>1000 clk)
+//                      of TMA latency covered; 2 residual/output buffers.
 template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 192 ? 3 : 4;
-  static constexpr int kNB = BN == 192 ? 2 : 4;          // in-place residual/output tile buffers
+  static constexpr int kStages = BN == 128 ? 5 : 4;
+  static constexpr int kNB = BN == 128 ? 2 : 4;          // in-place residual/output tile buffers
   static constexpr int kABytes = BM * BK * 2;            // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;            // 24 KB / 12 KB
+  static constexpr int kBBytes = BN * BK * 2;            // 16 KB / 12 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBoxes = BN / kBoxCols;           // 6 / 3
-  static constexpr int kOutBytes = kBoxes * kBoxBytes;   // 48 KB / 24 KB
-  static constexpr int kTmemCols = BN == 192 ? 512 : 256;
-  static constexpr int kChunk = BN / 6;                  // columns per tcgen05.ld of one epilogue thread (32 / 16)
+  static constexpr int kBoxes = BN / kBoxCols;           // 4 / 3
+  static constexpr int kOutBytes = kBoxes * kBoxBytes;   // 32 KB / 24 KB
+  static constexpr int kTmemCols = 256;                  // 2 accumulators of BN columns, power of two
+  static constexpr int kChunk = BN == 128 ? 32 : 16;     // columns per tcgen05.ld of one epilogue thread
+  static constexpr int kNumChunks = (BN / 2) / kChunk;   // 2 / 3
   static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
 };
 
@@ -218,15 +223,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       tc_fence_after();
       uint8_t *obuf = sOut + buf * C::kOutBytes;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hf * (BN / 2);
-      uint32_t r[3][C::kChunk];
+      uint32_t r[C::kNumChunks][C::kChunk];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < C::kNumChunks; ++c) {
         if constexpr (C::kChunk == 32) tmem_ld32(taddr + c * 32, r[c]);
         else tmem_ld16(taddr + c * 16, r[c]);
       }
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < C::kNumChunks; ++c) {
         const int col0 = hf * (BN / 2) + c * C::kChunk;          // first tile column of this chunk
 #pragma unroll
         for (int v = 0; v < C::kChunk / 8; ++v) {
@@ -377,8 +382,8 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
 int linear_tc(const LinearArgs &a, cudaStream_t st) {
   const int64_t m_tiles = (a.M + gemm::BM - 1) / gemm::BM;
   // wide tiles for compute-bound shapes (long K); narrow tiles + deeper output ring for memory-bound ones
-  const bool wide = (a.N % 192 == 0) && a.K >= 384 && m_tiles * (a.N / 192) >= num_sms();
-  return wide ? launch_tc<192>(a, st) : launch_tc<96>(a, st);
+  const bool wide = (a.N % 128 == 0) && a.K >= 384 && m_tiles * (a.N / 128) >= num_sms();
+  return wide ? launch_tc<128>(a, st) : launch_tc<96>(a, st);
 }
 
 }  // namespace mvit

@@ -21,6 +21,7 @@ namespace ptile {
 constexpr int TW = 8;
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
+constexpr int kStgPitch = 100;   // floats per staged column (96 + 4 pad: conflict-free 16-byte reads)
 
 template <typename T> struct IO;
 template <> struct IO<bf16> {
@@ -54,6 +55,7 @@ template <int S, int CPW> struct Geo {
   static constexpr int NR = (TH - 1) * MS + 3;          // compact input rows / cols of the halo tile
   static constexpr int NC = (TW - 1) * MS + 3;
   static constexpr int NPOS = NR * NC;
+  static constexpr int NPOS_PAD = (NPOS + 3) & ~3;     // keeps what follows the offset table 16-byte aligned
   static constexpr int WC = (CPW - 1) * MS + 3;         // compact cols one warp touches
 };
 
@@ -76,7 +78,9 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
   constexpr int FRAME = G::NPOS * PITCH;
   extern __shared__ __align__(16) uint8_t smem[];
   int *offs = reinterpret_cast<int *>(smem + kStages * FRAME);
-  float *w_s = reinterpret_cast<float *>(offs + G::NPOS);   // [96][27] staged copy of the filter
+  float *w_s = reinterpret_cast<float *>(offs + G::NPOS_PAD);   // [96][27] staged copy of the filter
+  float *gb_s = w_s + 96 * 27;                               // gamma[96] | beta[96]
+  float *stg = gb_s + 192 + (threadIdx.x >> 5) * (CPW * kStgPitch);   // this warp's [CPW][96 (+pad)] fp32 LN staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_h = blockIdx.x / tiles_w, tile_w = blockIdx.x % tiles_w;
@@ -92,6 +96,8 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
     offs[i] = (hin >= 0 && hin < p.H && win >= 0 && win < p.W) ? (int)((hin * p.W + win) * p.in_ls) : -1;
   }
   for (int i = threadIdx.x; i < 96 * 27; i += kThreads) w_s[i] = __ldg(weight + i);   // coalesced
+  for (int i = threadIdx.x; i < 192; i += kThreads)
+    gb_s[i] = p.has_ln ? (i < 96 ? __ldg(gamma + i) : __ldg(beta + i - 96)) : (i < 96 ? 1.f : 0.f);
   __syncthreads();
   // filter taps of this lane's channels: w[tap] = {c=2L, c=2L+1}, wz[tap] = c=64+L
   float2 wxy[27];
@@ -101,14 +107,6 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
     wxy[tap].x = w_s[(2 * lane) * 27 + tap];
     wxy[tap].y = w_s[(2 * lane + 1) * 27 + tap];
     wz[tap] = w_s[(64 + lane) * 27 + tap];
-  }
-  float2 gxy = make_float2(1.f, 1.f), bxy = make_float2(0.f, 0.f);
-  float gz = 1.f, bz = 0.f;
-  if (p.has_ln) {
-    gxy = make_float2(__ldg(gamma + 2 * lane), __ldg(gamma + 2 * lane + 1));
-    bxy = make_float2(__ldg(beta + 2 * lane), __ldg(beta + 2 * lane + 1));
-    gz = __ldg(gamma + 64 + lane);
-    bz = __ldg(beta + 64 + lane);
   }
   __syncthreads();
 
@@ -128,12 +126,17 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
   const int hl = CPW == 8 ? warp : (warp >> 1);          // output row of this warp inside the tile
   const int cl0 = CPW == 8 ? 0 : (warp & 1) * 4;         // first output column of this warp
   // rolling accumulators: a[0] -> output frame t-1, a[1] -> t, a[2] -> t+1 while input frame t is processed
+  // axy: channel pair {2L, 2L+1} of column j; az2: channel 64+L of the column PAIR (2jp, 2jp+1) so that it, too,
+  // is updated with packed FMAs
   float2 axy[3][CPW];
-  float az[3][CPW];
+  float2 az2[3][CPW / 2];
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < 3; ++k) {
 #pragma unroll
-    for (int j = 0; j < CPW; ++j) { axy[k][j] = make_float2(0.f, 0.f); az[k][j] = 0.f; }
+    for (int j = 0; j < CPW; ++j) axy[k][j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < CPW / 2; ++j) az2[k][j] = make_float2(0.f, 0.f);
+  }
 
   const int t_first = max(to0 - 1, 0), t_last = min(to1, p.T - 1);   // input frames needed (st == 1)
   // ring prologue: frames t_first .. t_first+kStages-2 in flight (one commit group per frame, empty if past the end)
@@ -157,64 +160,121 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const uint8_t *rowp = bufc + ((hl * G::MS + kh) * G::NC + cl0 * G::MS) * PITCH;
+      float2 xy[G::WC];
+      float z[G::WC];
 #pragma unroll
-      for (int cc = 0; cc < G::WC; ++cc) {
-        float2 xy;
-        float z;
-        IO<T>::load3(rowp + cc * PITCH, lane, xy, z);
+      for (int cc = 0; cc < G::WC; ++cc) IO<T>::load3(rowp + cc * PITCH, lane, xy[cc], z[cc]);
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          // which output column (if any) sees compact input col cc through tap kw
-          int j = -1;
-          if (S == 1) j = cc - kw;
-          else if (S == 2) j = ((cc - kw) % 2 == 0) ? (cc - kw) / 2 : -1;
-          else j = (cc % 3 == kw) ? cc / 3 : -1;
-          if (j >= 0 && j < CPW) {
+      for (int kw = 0; kw < 3; ++kw) {
+        // output column j sees compact input column cin(j, kw) through tap kw
 #pragma unroll
-            for (int kt = 0; kt < 3; ++kt) {
-              const int tap = (kt * 3 + kh) * 3 + kw;
-              // input frame t is tap kt of output frame t + 1 - kt  -> accumulator slot 2 - kt
-              axy[2 - kt][j] = __ffma2_rn(xy, wxy[tap], axy[2 - kt][j]);
-              az[2 - kt][j] = fmaf(z, wz[tap], az[2 - kt][j]);
-            }
+        for (int j = 0; j < CPW; ++j) {
+          const int cin = j * G::MS + kw;
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+            // input frame t is tap kt of output frame t + 1 - kt  -> accumulator slot 2 - kt
+            axy[2 - kt][j] = __ffma2_rn(xy[cin], wxy[(kt * 3 + kh) * 3 + kw], axy[2 - kt][j]);
+          }
+        }
+#pragma unroll
+        for (int jp = 0; jp < CPW / 2; ++jp) {
+          const float2 zz = make_float2(z[(2 * jp) * G::MS + kw], z[(2 * jp + 1) * G::MS + kw]);
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+            const float w1 = wz[(kt * 3 + kh) * 3 + kw];
+            az2[2 - kt][jp] = __ffma2_rn(zz, make_float2(w1, w1), az2[2 - kt][jp]);
           }
         }
       }
     }
-    // ---- output frame t-1 is complete (and frame t too when t is the last input frame)
+    // ---- output frame t-1 is complete (and frame t too when t is the last input frame).
+    // LayerNorm + store through a per-warp fp32 staging tile: the conv layout (lane = 3 channels of every column)
+    // is turned into "LPC lanes per column, 96/LPC contiguous channels each", so the two reductions cost
+    // log2(LPC) shuffles for ALL columns at once and every lane stores one contiguous, vectorised piece of a row.
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int to = pass == 0 ? t - 1 : t;
       const bool emit = to >= to0 && to < to1 && (pass == 0 || t == p.T - 1);
       if (emit) {
-        const int ho = ho0 + hl;
 #pragma unroll
         for (int j = 0; j < CPW; ++j) {
-          float2 v = pass == 0 ? axy[0][j] : axy[1][j];
-          float vz = pass == 0 ? az[0][j] : az[1][j];
-          if (p.has_ln) {
-            const float mean = warp_sum(v.x + v.y + vz) * (1.0f / 96.0f);
-            const float dx = v.x - mean, dy = v.y - mean, dz = vz - mean;
-            const float rstd = rsqrtf(warp_sum(dx * dx + dy * dy + dz * dz) * (1.0f / 96.0f) + p.eps);
-            v.x = dx * rstd * gxy.x + bxy.x;
-            v.y = dy * rstd * gxy.y + bxy.y;
-            vz = dz * rstd * gz + bz;
-          }
-          const int wo = wo0 + cl0 + j;
-          if (ho < p.Ho && wo < p.Wo) {
-            T *row = out + (int64_t)b * p.out_bs + (int64_t)((to * p.Ho + ho) * p.Wo + wo) * p.out_ls +
-                     (int64_t)head * p.out_hs;
-            IO<T>::store3(row, lane, v, vz);
+          *reinterpret_cast<float2 *>(stg + j * kStgPitch + 2 * lane) = pass == 0 ? axy[0][j] : axy[1][j];
+          const float2 zz = pass == 0 ? az2[0][j / 2] : az2[1][j / 2];
+          stg[j * kStgPitch + 64 + lane] = (j & 1) ? zz.y : zz.x;
+        }
+        __syncwarp();
+        constexpr int LPC = 32 / CPW;            // lanes per column: 4 or 8
+        constexpr int CH = 96 / LPC;             // channels per lane: 24 or 12
+        const int jc = lane / LPC, part = lane % LPC;
+        float x[CH];
+#pragma unroll
+        for (int k = 0; k < CH / 4; ++k) {
+          const float4 v = *reinterpret_cast<const float4 *>(stg + jc * kStgPitch + part * CH + 4 * k);
+          x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+        }
+        if (p.has_ln) {
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < CH; ++k) sum += x[k];
+#pragma unroll
+          for (int o = LPC / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float mean = sum * (1.0f / 96.0f);
+          float ss = 0.f;
+#pragma unroll
+          for (int k = 0; k < CH; ++k) { x[k] -= mean; ss = fmaf(x[k], x[k], ss); }
+#pragma unroll
+          for (int o = LPC / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          const float rstd = rsqrtf(ss * (1.0f / 96.0f) + p.eps);
+#pragma unroll
+          for (int k = 0; k < CH / 4; ++k) {
+            const float4 g = *reinterpret_cast<const float4 *>(gb_s + part * CH + 4 * k);
+            const float4 bt = *reinterpret_cast<const float4 *>(gb_s + 96 + part * CH + 4 * k);
+            x[4 * k] = fmaf(x[4 * k] * rstd, g.x, bt.x);
+            x[4 * k + 1] = fmaf(x[4 * k + 1] * rstd, g.y, bt.y);
+            x[4 * k + 2] = fmaf(x[4 * k + 2] * rstd, g.z, bt.z);
+            x[4 * k + 3] = fmaf(x[4 * k + 3] * rstd, g.w, bt.w);
           }
         }
+        const int ho = ho0 + hl, wo = wo0 + cl0 + jc;
+        if (ho < p.Ho && wo < p.Wo) {
+          T *row = out + (int64_t)b * p.out_bs + (int64_t)((to * p.Ho + ho) * p.Wo + wo) * p.out_ls +
+                   (int64_t)head * p.out_hs + part * CH;
+          if constexpr (sizeof(T) == 2) {
+            uint32_t w[CH / 2];
+#pragma unroll
+            for (int k = 0; k < CH / 2; ++k) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+              w[k] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            if constexpr (CH == 24) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                *reinterpret_cast<uint4 *>(row + 8 * k) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2 *>(row + 4 * k) = make_uint2(w[2 * k], w[2 * k + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < CH / 4; ++k)
+              *reinterpret_cast<float4 *>(row + 4 * k) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+          }
+        }
+        __syncwarp();   // staging is rewritten by the next emit
       }
     }
     // rotate: slot0 <- slot1 <- slot2 <- 0
 #pragma unroll
     for (int j = 0; j < CPW; ++j) {
-      axy[0][j] = axy[1][j]; az[0][j] = az[1][j];
-      axy[1][j] = axy[2][j]; az[1][j] = az[2][j];
-      axy[2][j] = make_float2(0.f, 0.f); az[2][j] = 0.f;
+      axy[0][j] = axy[1][j];
+      axy[1][j] = axy[2][j];
+      axy[2][j] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < CPW / 2; ++j) {
+      az2[0][j] = az2[1][j];
+      az2[1][j] = az2[2][j];
+      az2[2][j] = make_float2(0.f, 0.f);
     }
     slot = (slot + 1) % kStages;
   }
@@ -224,7 +284,8 @@ template <typename T, int S, int CPW>
 static int launch(const void *in, const float *w, const float *g, const float *b, void *out, const PoolParams &p,
                   cudaStream_t st) {
   using G = Geo<S, CPW>;
-  const size_t smem = Ring<T>::kStages * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS * sizeof(int) + 96 * 27 * sizeof(float);
+  const size_t smem = Ring<T>::kStages * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS_PAD * sizeof(int) +
+                      (96 * 27 + 192 + kWarps * CPW * kStgPitch) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     MVIT_CUDA_OK(cudaFuncSetAttribute(pool_tiled_kernel<T, S, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -268,7 +329,7 @@ int pool_tiled_try(const void *in, const float *w, const float *g, const float *
   const int64_t es = dtype == MVIT_BF16 ? 2 : 4;
   auto al = [&](int64_t elems) { return (elems * es) % 16 == 0; };
   if ((reinterpret_cast<uintptr_t>(in) & 15) || !al(p.in_bs) || !al(p.in_ls) || !al(p.in_hs)) return 1;
-  if ((reinterpret_cast<uintptr_t>(out) & 7) || (p.out_bs * es) % 8 || (p.out_ls * es) % 8 || (p.out_hs * es) % 8) return 1;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (p.out_bs * es) % 16 || (p.out_ls * es) % 16 || (p.out_hs * es) % 16) return 1;
   if (dtype == MVIT_BF16) return ptile::dispatch<bf16>(in, w, g, b, out, p, st);
   return ptile::dispatch<float>(in, w, g, b, out, p, st);
 }
