@@ -30,21 +30,25 @@ constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 384
 constexpr int kBoxCols = 32;               // output / residual boxes: 128 rows x 32 cols (64 B), SWIZZLE_64B
 constexpr int kBoxBytes = BM * kBoxCols * 2;
 
-// Two tile shapes:
-//   BN = 96  "narrow": memory-bound shapes (K <= 192): 4 operand stages, 4 in-place residual/output buffers;
-//   BN = 128 "wide":   compute-bound shapes (K >= 384): 5 operand stages of 32 KB keep ~4 k-blocks (>1000 clk)
-//                      of TMA latency covered; 2 residual/output buffers.
-template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 128 ? 5 : 4;
-  static constexpr int kNB = BN == 128 ? 2 : 4;          // in-place residual/output tile buffers
-  static constexpr int kABytes = BM * BK * 2;            // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;            // 16 KB / 12 KB
+// Three tile configurations:
+//   <96,  false> "narrow": memory-bound shapes (K <= 192): 4 operand stages, 4 in-place residual/output buffers;
+//   <128, false> "wide":   compute-bound shapes whose N is not a multiple of 192;
+//   <192, true>  "pair":   compute-bound shapes: a 2-CTA cluster computes a 256 x 192 tile with
+//                tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of x and HALF (96 rows) of the w
+//                tile, so operand traffic from L2 per FLOP drops by 1.75x (the 1-CTA kernel is L2->SM bound at
+//                ~64 FLOP/B); accumulators live in both CTAs' TMEM, each CTA drains/stores its own 128 rows.
+template <int BN, bool PAIR> struct Cfg {
+  static constexpr int kStages = PAIR ? 4 : (BN == 128 ? 5 : 4);
+  static constexpr int kNB = (PAIR || BN == 128) ? 2 : 4;  // in-place residual/output tile buffers
+  static constexpr int kABytes = BM * BK * 2;              // 16 KB
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;        // w rows staged by one CTA
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBoxes = BN / kBoxCols;           // 4 / 3
-  static constexpr int kOutBytes = kBoxes * kBoxBytes;   // 32 KB / 24 KB
-  static constexpr int kTmemCols = 256;                  // 2 accumulators of BN columns, power of two
-  static constexpr int kChunk = BN == 128 ? 32 : 16;     // columns per tcgen05.ld of one epilogue thread
-  static constexpr int kNumChunks = (BN / 2) / kChunk;   // 2 / 3
+  static constexpr int kBoxes = BN / kBoxCols;
+  static constexpr int kOutBytes = kBoxes * kBoxBytes;
+  static constexpr int kTmemCols = BN == 192 ? 512 : 256;  // 2 accumulators of BN columns, power of two
+  static constexpr int kChunk = BN == 96 ? 16 : 32;        // columns per tcgen05.ld of one epilogue thread
+  static constexpr int kNumChunks = (BN / 2) / kChunk;     // 3 / 2 / 3
   static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
 };
 
@@ -72,11 +76,11 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   return __ffma2_rn(x, phi, __fmul2_rn(x, make_float2(0.5f, 0.5f)));
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sA = smem;
@@ -89,8 +93,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(buf_free + C::kNB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PAIR: the two CTAs of a cluster walk the same sequence of 256-row tiles; CTA `rank` owns rows [128*rank, +128)
+  constexpr int TM = PAIR ? 2 * BM : BM;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const int64_t tile0 = PAIR ? blockIdx.x / 2 : blockIdx.x, tile_step = PAIR ? gridDim.x / 2 : gridDim.x;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int64_t m_tiles = (p.M + BM - 1) / BM;
+  const int64_t m_tiles = (p.M + TM - 1) / TM;
   const int64_t tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
 
@@ -107,7 +115,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
+      mbar_init(&tempty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);   // PAIR: both CTAs' epilogues release the leader
     }
     for (int i = 0; i < C::kNB; ++i) {
       mbar_init(&res_full[i], 1);
@@ -116,11 +124,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, C::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // barriers of BOTH CTAs are initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -129,27 +143,34 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * BN;
+      for (int64_t t = tile0; t < tiles; t += tile_step) {
+        const int m0 = (int)(t / n_tiles) * TM + (int)rank * BM, n0 = (int)(t % n_tiles) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-          tma_load_2d(sA + stage * C::kABytes, &tmap_x, &full[stage], kb * BK, m0);
-          tma_load_2d(sB + stage * C::kBBytes, &tmap_w, &full[stage], kb * BK, n0);
+          if constexpr (PAIR) {
+            // both CTAs' bytes land on the leader's barrier; the leader arms it for the whole 2-CTA stage
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+            tma_load_2d_pair(sA + stage * C::kABytes, &tmap_x, &full[stage], kb * BK, m0);
+            tma_load_2d_pair(sB + stage * C::kBBytes, &tmap_w, &full[stage], kb * BK, n0 + (int)rank * C::kBRows);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+            tma_load_2d(sA + stage * C::kABytes, &tmap_x, &full[stage], kb * BK, m0);
+            tma_load_2d(sB + stage * C::kBBytes, &tmap_w, &full[stage], kb * BK, n0);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+      for (int64_t t = tile0; t < tiles; t += tile_step) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);       // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -160,12 +181,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(a0 + k * UMMA_K * 2, 16, 1024, SWZ_128B);
             const uint64_t db = make_smem_desc(b0 + k * UMMA_K * 2, 16, 1024, SWZ_128B);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+            else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);                 // smem slot free once these MMAs have read it
+          // smem slot free (in both CTAs) once these MMAs have read it
+          if constexpr (PAIR) umma_commit_pair(&empty[stage], 0b11);
+          else umma_commit(&empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);                     // accumulator complete
+        if constexpr (PAIR) umma_commit_pair(&tfull[acc], 0b11);   // accumulator complete (both halves)
+        else umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -174,10 +199,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       int buf = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int64_t t = tile0; t < tiles; t += tile_step) {
         mbar_wait(&buf_free[buf], phase ^ 1);         // the TMA store that last used this buffer has read it
         if (p.has_residual) {
-          const int64_t mrow = (t / n_tiles) * BM;
+          const int64_t mrow = (t / n_tiles) * TM + rank * BM;
           const int m0 = (int)(p.res_period ? mrow % p.res_period : mrow), n0 = (int)(t % n_tiles) * BN;
           mbar_arrive_expect_tx(&res_full[buf], C::kOutBytes);
 #pragma unroll
@@ -202,15 +227,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int64_t it = 0;
     // bias slice of the first tile; later slices are fetched one tile ahead (global latency off the critical path)
     if (et < BN) {
-      const int n = (int)(blockIdx.x % n_tiles) * BN + et;
-      sBias[et] = (p.bias && blockIdx.x < tiles && n < p.N) ? p.bias[n] : 0.f;
+      const int n = (int)(tile0 % n_tiles) * BN + et;
+      sBias[et] = (p.bias && tile0 < tiles && n < p.N) ? p.bias[n] : 0.f;
     }
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-      const int64_t m0 = (t / n_tiles) * BM;
+    for (int64_t t = tile0; t < tiles; t += tile_step, ++it) {
+      const int64_t m0 = (t / n_tiles) * TM + rank * BM;
       const int n0 = (int)(t % n_tiles) * BN;
       const float *bias_s = sBias + (it & 1) * BN;
       float bias_next = 0.f;
-      const int64_t tn = t + gridDim.x;
+      const int64_t tn = t + tile_step;
       if (et < BN && tn < tiles && p.bias) {
         const int n = (int)(tn % n_tiles) * BN + et;
         if (n < p.N) bias_next = p.bias[n];
@@ -274,7 +299,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // accumulator fully read -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA warp owns the accumulators
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       // tile is complete in shared memory -> one thread TMA-stores it
       fence_proxy_async_smem();
@@ -294,8 +322,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (et == 0) tma_store_wait_all<0>();              // global writes complete before the CTA retires
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if constexpr (PAIR) {
+    cluster_sync_all();                                // both CTAs are done with TMEM, smem and remote barriers
+    if (warp == 2) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
 }  // namespace gemm
@@ -345,9 +378,9 @@ bool linear_tc_supported(const LinearArgs &a, const char **why) {
   return true;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_tc(const LinearArgs &a, cudaStream_t st) {
-  using C = gemm::Cfg<BN>;
+  using C = gemm::Cfg<BN, PAIR>;
   CUtensorMap tx, tw, ty, tr;
   auto enc2 = [&](CUtensorMap *m, const void *ptr, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t bc,
                   uint32_t br, CUtensorMapSwizzle sw) {
@@ -358,7 +391,7 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   };
   int r;
   if ((r = enc2(&tx, a.x, a.K, a.M, a.K, gemm::BK, gemm::BM, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
-  if ((r = enc2(&tw, a.w, a.K, a.N, a.K, gemm::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  if ((r = enc2(&tw, a.w, a.K, a.N, a.K, gemm::BK, C::kBRows, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
   if ((r = enc2(&ty, a.y, a.N, a.M, a.ldy, gemm::kBoxCols, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
   if (a.residual) {
     const uint64_t res_rows = a.res_period ? (uint64_t)a.res_period : (uint64_t)a.M;
@@ -368,22 +401,38 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
   gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0};
-  const int64_t tiles = ((a.M + gemm::BM - 1) / gemm::BM) * ((a.N + BN - 1) / BN);
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
-  gemm::linear_tc_kernel<BN><<<grid, gemm::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
-  MVIT_LAUNCH_OK("linear(tcgen05)");
+  constexpr int TM = PAIR ? 2 * gemm::BM : gemm::BM;
+  const int64_t tiles = ((a.M + TM - 1) / TM) * ((a.N + BN - 1) / BN);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(tiles, num_sms() / 2));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)std::min<int64_t>(tiles, num_sms()));
+  }
+  cfg.blockDim = dim3(gemm::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  MVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm::linear_tc_kernel<BN, PAIR>, tx, tw, ty, tr, p));
   return 0;
 }
 
 int linear_tc(const LinearArgs &a, cudaStream_t st) {
-  const int64_t m_tiles = (a.M + gemm::BM - 1) / gemm::BM;
-  // wide tiles for compute-bound shapes (long K); narrow tiles + deeper output ring for memory-bound ones
-  const bool wide = (a.N % 128 == 0) && a.K >= 384 && m_tiles * (a.N / 128) >= num_sms();
-  return wide ? launch_tc<128>(a, st) : launch_tc<96>(a, st);
+  // compute-bound shapes (long K): CTA pairs on 256x192 tiles, else 128x128; memory-bound shapes: 128x96 tiles
+  // with a deeper output ring
+  if (a.K >= 384 && a.N % 192 == 0 && ((a.M + 255) / 256) * (a.N / 192) >= num_sms() / 2) return launch_tc<192, true>(a, st);
+  if (a.K >= 384 && a.N % 128 == 0 && ((a.M + 127) / 128) * (a.N / 128) >= num_sms()) return launch_tc<128, false>(a, st);
+  return launch_tc<96, false>(a, st);
 }
 
 }  // namespace mvit
