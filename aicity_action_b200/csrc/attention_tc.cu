@@ -8,7 +8,7 @@
 //               one of the stream's TWO score buffers in TMEM, and O += P·V (tcgen05.mma TS: P from TMEM,
 //               V MN-major from smem, N96 K16 x4).  Because S is double-buffered, QKᵀ of tile j+1 is issued
 //               before the softmax of tile j finishes: the softmax warps never wait for the tensor pipe.
-//   warp 2      TMEM allocator (S00 S01 S10 S11 | O0 O1 = 448 of 512 columns);
+//   warp 2      TMEM allocator (S00 S01 S10 S11 | O0 O1 = 480 of 512 columns); also writes the constant ones chunk;
 //   warps 4-7 / 8-11  softmax of stream 0 / 1: thread = query row (TMEM lane); one pass per tile against the
 //               running (possibly stale) maximum — exp2 domain, 3/4 of the exponentials on MUFU and 1/4 on the
 //               FMA pipe (Cody-Waite + cubic), bf16 packing on the integer pipe, tile maximum reduced on the
@@ -28,11 +28,17 @@ constexpr int kQChunkBytes = BQ * kChunkCols * 2;    // 8 KB: 128 rows x 64 B, S
 constexpr int kQTileBytes = kChunks * kQChunkBytes;  // 24 KB
 constexpr int kKChunkBytes = BKV * kChunkCols * 2;   // 4 KB:  64 rows x 64 B
 constexpr int kKTileBytes = kChunks * kKChunkBytes;  // 12 KB
+// V is staged with a 4th, constant 32-column chunk whose column 0 is all ones: the P·V MMA (N = 112) then also
+// accumulates the softmax denominator l = sum_j P_ij in accumulator column 96 — with exactly the bf16 values the
+// tensor core multiplies, so no row-sum arithmetic is left in the softmax warps.
+constexpr int kVTileBytes = (kChunks + 1) * kKChunkBytes;   // 16 KB
+constexpr int kStageBytes = kKTileBytes + kVTileBytes;      // 28 KB
 constexpr int kStages = 6;
 constexpr int kThreads = 384;
-constexpr int kSmemBytes = 2 * kQTileBytes + kStages * 2 * kKTileBytes + 512 + 1024;
+constexpr int kSmemBytes = 2 * kQTileBytes + kStages * kStageBytes + 512 + 1024;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256;           // S[i][b] at 128*i + 64*b, O_i at 256 + 96*i
+constexpr int DO = D + 16;                           // accumulator columns per stream: 96 outputs + denominator (+pad)
+constexpr uint32_t kColS = 0, kColO = 256;           // S[i][b] at 128*i + 64*b, O_i at 256 + 112*i
 constexpr float kRescaleThreshold = 8.0f;            // log2 units
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, no range fix-ups
@@ -78,7 +84,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sQ = smem;                                  // [2][24 KB]
   uint8_t *sKV = smem + 2 * kQTileBytes;               // [stage][K 12 KB | V 12 KB]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * 2 * kKTileBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * kStageBytes);
   uint64_t *q_full = bars;                 // 1
   uint64_t *k_full = bars + 1;             // kStages
   uint64_t *v_full = k_full + kStages;     // kStages
@@ -118,6 +124,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  if (warp == 3) {
+    // constant "ones" chunk of every V stage: [64 kv rows][32 cols] bf16, 64B-swizzled; logical column 0 = 1.0
+    for (int st = 0; st < kStages; ++st) {
+      uint4 *chunk = reinterpret_cast<uint4 *>(sKV + st * kStageBytes + kKTileBytes + kChunks * kKChunkBytes);
+      for (int i = lane; i < kKChunkBytes / 16; i += 32) {
+        const int r = i >> 2, c16 = i & 3;                       // row, physical 16-byte slot
+        chunk[i] = make_uint4(c16 == ((r >> 1) & 3) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+      }
+    }
+    fence_proxy_async_smem();                                    // generic-proxy writes -> visible to tcgen05.mma
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -136,7 +153,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int s = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t *kdst = sKV + s * 2 * kKTileBytes, *vdst = kdst + kKTileBytes;
+        uint8_t *kdst = sKV + s * kStageBytes, *vdst = kdst + kKTileBytes;
         mbar_arrive_expect_tx(&k_full[s], kKTileBytes);
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(kdst + c * kKChunkBytes, &tmap_k, &k_full[s], c * kChunkCols, j * BKV, bh);
@@ -149,11 +166,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int i = warp == 1 ? 0 : 1;
       if (i == 0 || two) {
         constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
-        constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // A = P (TMEM),    B = V (MN-major)
+        constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DO, 0, 1);    // A = P (TMEM),    B = [V | 1] (MN-major)
         const uint32_t sq = smem_u32(sQ) + i * kQTileBytes, skv = smem_u32(sKV);
-        const uint32_t tS_i = tmem_base + kColS + i * 128, tO_i = tmem_base + kColO + i * D;
+        const uint32_t tS_i = tmem_base + kColS + i * 128, tO_i = tmem_base + kColO + i * DO;
         auto issue_qk = [&](int s, int b) {
-          const uint32_t k0 = skv + s * 2 * kKTileBytes;
+          const uint32_t k0 = skv + s * kStageBytes;
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint32_t step = (k & 1) * 32;
@@ -163,7 +180,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           umma_commit(&s_full[i * 2 + b]);
         };
         auto issue_pv = [&](int s, int b, bool accumulate) {
-          const uint32_t v0 = skv + s * 2 * kKTileBytes + kKTileBytes;
+          const uint32_t v0 = skv + s * kStageBytes + kKTileBytes;
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             // V tile: [64 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
@@ -203,9 +220,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int row = q0 + i * BQ + quarter * 32 + lane;
       const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
       const uint32_t tS_i = tmem_base + lane_base + kColS + i * 128;
-      const uint32_t tO = tmem_base + lane_base + kColO + i * D;
+      const uint32_t tO = tmem_base + lane_base + kColO + i * DO;
       const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
-      float m_used = -INFINITY, l_run = 0.f;
+      float m_used = -INFINITY;
       for (int j = 0; j < nkv; ++j) {
         const int b = j & 1;
         const uint32_t tS = tS_i + b * BKV;
@@ -234,10 +251,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // One pass: P = exp2(s*scale_log2 - m_used) against the running (possibly stale) maximum while the tile
         // maximum is reduced on the side; max / exp / sum / pack of different elements are independent, so the
         // ALU, FMA and MUFU pipes overlap.
-        float psum = 0.f;
         auto softmax_pass = [&](float m_ref) -> float {
           const float2 nm2 = make_float2(-m_ref, -m_ref);
-          float2 psum2 = make_float2(0.f, 0.f);
           float mx0 = -INFINITY, mx1 = -INFINITY;
           uint32_t pk[32];
 #pragma unroll
@@ -248,11 +263,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             else mx0 = fmaxf(mx0, fmaxf(s0, s1));
             const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
             const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-            psum2 = __fadd2_rn(psum2, pe);
-            pk[e] = pack_bf16x2_alu(pe.x, pe.y);
+            // bf16 by truncation (one PRMT): numerator and denominator both come from these exact values through
+            // the same MMA, so the truncation bias cancels in O / l
+            pk[e] = __byte_perm(__float_as_uint(pe.x), __float_as_uint(pe.y), 0x7632);
           }
           tmem_st32(tS, pk);                          // P (bf16) over the first 32 columns of this score buffer
-          psum = psum2.x + psum2.y;
           return fmaxf(mx0, mx1) * p.scale_log2;
         };
         const float m_tile = softmax_pass(m_used);
@@ -263,7 +278,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_wait(&o_done[i], (j - 1) & 1);       // PV(j-1) has landed in O
             tc_fence_after();
             const float alpha = ex2_approx(m_used - m_new);
-            l_run *= alpha;
             m_used = m_new;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -274,11 +288,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
               tmem_st32(tO + c * 32, o);
             }
+            {
+              uint32_t o[16];                         // column 96 = running denominator (97..111 are zero)
+              tmem_ld16(tO + 96, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st16(tO + 96, o);
+            }
             tmem_st_wait();
             softmax_pass(m_used);
           }
         }
-        l_run += psum;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[i * 2 + b]);
@@ -286,6 +307,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // ---- epilogue: O / l (+ q) -> out[b, row, head*96 + :]
       mbar_wait(&o_done[i], (nkv - 1) & 1);
       tc_fence_after();
+      float l_run;
+      {
+        uint32_t o[16];
+        tmem_ld16(tO + 96, o);
+        tmem_ld_wait();
+        l_run = __uint_as_float(o[0]);
+      }
       const float inv = 1.0f / l_run;
       const int b = bh / p.heads, head = bh % p.heads;
       const bool live = row < p.Lq;
