@@ -126,6 +126,65 @@ static int dispatch_generic(const void *in, const float *w, const float *g, cons
   MVIT_REQUIRE(false, "attention_pool: head_dim %d unsupported (need 32..128, multiple of 32)", p.d);
 }
 
+
+// Channels-last MaxPool3d for the skip path (attention.py:427-432: MaxPool3d([1,3,3],[1,2,2],[0,1,1]) on [B, L, C]):
+// one thread = 8 consecutive channels (one 16-byte vector) of one output token; the window's vectors are read
+// with coalesced 16-byte loads and reduced with packed bf16 max.  Memory-bound: every input byte is read ~2.25x
+// through L1/L2, once from HBM.
+__global__ void __launch_bounds__(256) maxpool_tokens_bf16_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out,
+                                                                 PoolParams p, int C) {
+  const int vecs = C / 8;
+  const int64_t total = (int64_t)p.B * p.To * p.Ho * p.Wo * vecs;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = (int)(i % vecs);
+    int64_t r = i / vecs;
+    const int wo = (int)(r % p.Wo); r /= p.Wo;
+    const int ho = (int)(r % p.Ho); r /= p.Ho;
+    const int to = (int)(r % p.To);
+    const int b = (int)(r / p.To);
+    const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+    __nv_bfloat162 m[4] = {ninf, ninf, ninf, ninf};
+    const bf16 *src = in + (int64_t)b * p.in_bs + v * 8;
+    for (int a = 0; a < p.kt; ++a) {
+      const int t = t0 + a;
+      if (t < 0 || t >= p.T) continue;
+      for (int bq = 0; bq < p.kh; ++bq) {
+        const int h = h0 + bq;
+        if (h < 0 || h >= p.H) continue;
+        for (int c = 0; c < p.kw; ++c) {
+          const int w = w0 + c;
+          if (w < 0 || w >= p.W) continue;
+          const uint4 x = *reinterpret_cast<const uint4 *>(src + (int64_t)((t * p.H + h) * p.W + w) * p.in_ls);
+          const __nv_bfloat162 *xv = reinterpret_cast<const __nv_bfloat162 *>(&x);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], xv[k]);
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 *ov = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ov[k] = m[k];
+    *reinterpret_cast<uint4 *>(out + (int64_t)b * p.out_bs + (int64_t)((to * p.Ho + ho) * p.Wo + wo) * p.out_ls + v * 8) = o;
+  }
+}
+
+// returns 1 when it does not apply
+static int maxpool_tokens_try(const void *in, void *out, const PoolParams &p, int mode, int dtype, cudaStream_t st) {
+  if (mode != MVIT_POOL_MAX || dtype != MVIT_BF16 || p.has_cls || p.has_ln) return 1;
+  const int C = p.heads * p.d;
+  // only the plain [B, L, C] -> [B, L', C] layout (heads are consecutive d-channel groups of a token)
+  if (p.in_hs != p.d || p.out_hs != p.d || p.in_ls != C || p.out_ls != C || C % 8 != 0) return 1;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (p.in_bs % 8) || (p.out_bs % 8)) return 1;
+  const int64_t total = (int64_t)p.B * p.To * p.Ho * p.Wo * (C / 8);
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+  maxpool_tokens_bf16_kernel<<<blocks, 256, 0, st>>>(static_cast<const bf16 *>(in), static_cast<bf16 *>(out), p, C);
+  MVIT_LAUNCH_OK("attention_pool(maxpool tokens)");
+  return 0;
+}
+
 }  // namespace mvit
 
 extern "C" int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
@@ -160,6 +219,8 @@ extern "C" int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in
   p.eps = eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int r = pool_tiled_try(in, weight, gamma, beta, out, p, mode, dtype, s);
+  if (r <= 0) return r;
+  r = maxpool_tokens_try(in, out, p, mode, dtype, s);
   if (r <= 0) return r;
   if (dtype == MVIT_F32) return dispatch_generic<float>(in, weight, gamma, beta, out, p, mode, s);
   return dispatch_generic<bf16>(in, weight, gamma, beta, out, p, mode, s);
