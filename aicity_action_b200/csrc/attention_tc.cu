@@ -9,13 +9,14 @@
 //               V MN-major from smem, N96 K16 x4).  Because S is double-buffered, QKᵀ of tile j+1 is issued
 //               before the softmax of tile j finishes: the softmax warps never wait for the tensor pipe.
 //   warp 2      TMEM allocator (S00 S01 S10 S11 | O0 O1 = 480 of 512 columns); also writes the constant ones chunk;
-//   warps 4-11 / 12-19  softmax of stream 0 / 1, TWO threads per query row (each owns 32 of the tile's 64 keys;
-//               4 warps per scheduler keep the issue slots full): one pass per tile against the running maximum
-//               — exp2 domain, 3/4 of the exponentials on MUFU and 1/4 on the FMA pipe (Cody-Waite + cubic), bf16
-//               packing on the integer pipe, tile maximum reduced on the side and exchanged with the partner
-//               thread through shared memory; O is rescaled only when a row maximum grew by more than 2^8.
-//               P (bf16) overwrites the first half of the thread's own score columns with tcgen05.st.  At the
-//               end the warps normalise O, add the pooled-q residual and store [B, Lq, heads*96] directly.
+//   warps 4-7 / 8-11  softmax of stream 0 / 1: thread = query row (TMEM lane); one pass per tile against the
+//               running (possibly stale) maximum — exp2 domain, 3/4 of the exponentials on MUFU and 1/4 on the
+//               FMA pipe (Cody-Waite + cubic), bf16 packing on the integer pipe, tile maximum reduced on the
+//               side; O is rescaled (and the pass repeated) only when a row maximum grew by more than 2^8.
+//               P (bf16) overwrites the first 32 columns of its score buffer with tcgen05.st.  At the end the
+//               warps normalise O, add the pooled-q residual and store [B, Lq, heads*96] directly.
+#include <stdlib.h>
+
 #include "attention.cuh"
 #include "tc_common.cuh"
 
@@ -35,9 +36,8 @@ constexpr int kKTileBytes = kChunks * kKChunkBytes;  // 12 KB
 constexpr int kVTileBytes = (kChunks + 1) * kKChunkBytes;   // 16 KB
 constexpr int kStageBytes = kKTileBytes + kVTileBytes;      // 28 KB
 constexpr int kStages = 6;
-constexpr int kThreads = 640;                       // 4 control warps + 2 streams x 8 softmax warps
-constexpr int kMaxBytes = 2 * 2 * 2 * 128 * 4;       // row-max exchange: [parity][stream][half][row] fp32
-constexpr int kSmemBytes = 2 * kQTileBytes + kStages * kStageBytes + kMaxBytes + 512 + 1024;
+constexpr int kThreads = 384;
+constexpr int kSmemBytes = 2 * kQTileBytes + kStages * kStageBytes + 512 + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr int DO = D + 16;                           // accumulator columns per stream: 96 outputs + denominator (+pad)
 constexpr uint32_t kColS = 0, kColO = 256;           // S[i][b] at 128*i + 64*b, O_i at 256 + 112*i
@@ -79,6 +79,8 @@ struct Params {
   float scale_log2;   // scale * log2(e)
 };
 
+// POLY: how many of every 4 score pairs take the FMA-pipe exp2 (0 = all MUFU, 1 = 25 %, 2 = 50 %)
+template <int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, Params p) {
@@ -86,8 +88,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sQ = smem;                                  // [2][24 KB]
   uint8_t *sKV = smem + 2 * kQTileBytes;               // [stage][K 12 KB | V 12 KB]
-  float *sMax = reinterpret_cast<float *>(sKV + kStages * kStageBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * kStageBytes + kMaxBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * kStageBytes);
   uint64_t *q_full = bars;                 // 1
   uint64_t *k_full = bars + 1;             // kStages
   uint64_t *v_full = k_full + kStages;     // kStages
@@ -117,7 +118,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 256);
+      mbar_init(&p_ready[i], 128);
     }
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
@@ -144,6 +145,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {
       // -------------------------------------------------------------- TMA producer
       const int ntile = two ? 2 : 1;
@@ -186,9 +188,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             // V tile: [64 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
-            // P of keys [32h, 32h+32) sits in the first 16 columns of that half's own score columns
-            umma_ts(tO_i, tS_i + b * BKV + (k >> 1) * 32 + (k & 1) * 8,
-                    make_smem_desc(v0 + k * 16 * 64, kKChunkBytes, 512, SWZ_64B), idesc_pv, (accumulate || k != 0));
+            umma_ts(tO_i, tS_i + b * BKV + k * 8, make_smem_desc(v0 + k * 16 * 64, kKChunkBytes, 512, SWZ_64B),
+                    idesc_pv, (accumulate || k != 0));
           }
           umma_commit(&o_done[i]);
         };
@@ -215,139 +216,140 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax warps
-    const int sw = warp - 4;
-    const int i = sw >> 3;                            // stream
-    const int quarter = sw & 3;                       // TMEM lane quarter this warp may touch (== warp % 4)
-    const int h = (sw >> 2) & 1;                      // which 32 keys of every 64-key tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ---------------------------------------------------------------- softmax warpgroups
+    const int i = (warp - 4) >> 2;                    // stream
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may touch
     if (i == 0 || two) {
-      const int r128 = quarter * 32 + lane;           // row inside the stream's 128-row tile
-      const int row = q0 + i * BQ + r128;
+      const int row = q0 + i * BQ + quarter * 32 + lane;
       const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-      const uint32_t tS_i = tmem_base + lane_base + kColS + i * 128 + h * 32;
+      const uint32_t tS_i = tmem_base + lane_base + kColS + i * 128;
       const uint32_t tO = tmem_base + lane_base + kColO + i * DO;
       const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
-      const int pair_bar = 1 + i * 4 + quarter;       // named barrier shared by the two warps of this row group
-      float *my_max = sMax + (i * 2 + h) * 128 + r128, *peer_max = sMax + (i * 2 + (h ^ 1)) * 128 + r128;
-      auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
       float m_used = -INFINITY;
       for (int j = 0; j < nkv; ++j) {
         const int b = j & 1;
         const uint32_t tS = tS_i + b * BKV;
-        const int par = (j & 1) * 512;                // double-buffered exchange slot
         mbar_wait(&s_full[i * 2 + b], (j >> 1) & 1);
         tc_fence_after();
-        uint32_t s[32];
-        tmem_ld32(tS, s);
+        uint32_t s[2][32];
+        tmem_ld32(tS, s[0]);
+        tmem_ld32(tS + 32, s[1]);
         tmem_ld_wait();
-        const int valid = p.Lk - j * BKV - h * 32;    // keys of this half that exist (may be <= 0 in the last tile)
-        if (valid < 32) {
+        const int valid = p.Lk - j * BKV;             // >= 1
+        if (valid < BKV) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e >= valid) s[e] = 0xff800000u;       // -inf
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e >= valid) s[c][e] = 0xff800000u;   // -inf
         }
         if (j == 0) {                                 // first tile: the reference maximum is this tile's own
           float mx = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[e]));
-          my_max[512] = mx;                           // slot of parity 1 (tile 0 itself publishes into parity 0)
-          pair_sync();
-          m_used = fmaxf(mx, peer_max[512]) * p.scale_log2;
-        }
-        // One pass: P = exp2(s*scale_log2 - m_used) against the running (possibly stale) maximum while this half's
-        // tile maximum is reduced on the side; max / exp / pack of different elements are independent.
-        const float2 nm2 = make_float2(-m_used, -m_used);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        uint32_t pk[16];
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float s0 = __uint_as_float(s[2 * e]), s1 = __uint_as_float(s[2 * e + 1]);
-          if (e & 1) mx1 = fmaxf(mx1, fmaxf(s0, s1));
-          else mx0 = fmaxf(mx0, fmaxf(s0, s1));
-          const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
-          const float2 pe = ((e & 3) == 3) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-          // bf16 by truncation (one PRMT): numerator and denominator both come from these exact values through
-          // the same MMA, so the truncation bias cancels in O / l
-          pk[e] = __byte_perm(__float_as_uint(pe.x), __float_as_uint(pe.y), 0x7632);
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[c][e]));
+          m_used = mx * p.scale_log2;
         }
-        tmem_st16(tS, pk);                            // P (bf16) over the first 16 of this thread's own S columns
-        my_max[par] = fmaxf(mx0, mx1);
+        // One pass: P = exp2(s*scale_log2 - m_used) against the running (possibly stale) maximum while the tile
+        // maximum is reduced on the side; max / exp / sum / pack of different elements are independent, so the
+        // ALU, FMA and MUFU pipes overlap.
+        auto softmax_pass = [&](float m_ref) -> float {
+          const float2 nm2 = make_float2(-m_ref, -m_ref);
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          uint32_t pk[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int c = e >> 4, idx = (e & 15) * 2;
+            const float s0 = __uint_as_float(s[c][idx]), s1 = __uint_as_float(s[c][idx + 1]);
+            if (e & 1) mx1 = fmaxf(mx1, fmaxf(s0, s1));
+            else mx0 = fmaxf(mx0, fmaxf(s0, s1));
+            const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
+            const bool poly = POLY == 2 ? (e & 1) == 1 : (POLY == 1 ? (e & 3) == 3 : false);
+            const float2 pe = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            // bf16 by truncation (one PRMT): numerator and denominator both come from these exact values through
+            // the same MMA, so the truncation bias cancels in O / l
+            pk[e] = __byte_perm(__float_as_uint(pe.x), __float_as_uint(pe.y), 0x7632);
+          }
+          tmem_st32(tS, pk);                          // P (bf16) over the first 32 columns of this score buffer
+          return fmaxf(mx0, mx1) * p.scale_log2;
+        };
+        const float m_tile = softmax_pass(m_used);
+        if (j > 0) {
+          const float m_new = fmaxf(m_used, m_tile);
+          const bool need = (m_new - m_used) > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {        // rare (first tiles): rescale O, then redo the pass
+            mbar_wait(&o_done[i], (j - 1) & 1);       // PV(j-1) has landed in O
+            tc_fence_after();
+            const float alpha = ex2_approx(m_used - m_new);
+            m_used = m_new;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            {
+              uint32_t o[16];                         // column 96 = running denominator (97..111 are zero)
+              tmem_ld16(tO + 96, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st16(tO + 96, o);
+            }
+            tmem_st_wait();
+            softmax_pass(m_used);
+          }
+        }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[i * 2 + b]);
-        // agree with the partner thread on the row maximum seen so far; a growth beyond the threshold rescales O
-        // after PV(j) (every contribution accumulated so far, tile j included, is relative to the old maximum)
-        pair_sync();
-        const float m_new = fmaxf(m_used, fmaxf(my_max[par], peer_max[par]) * p.scale_log2);
-        const bool need = (m_new - m_used) > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need) && j + 1 < nkv) {
-          mbar_wait(&o_done[i], j & 1);               // PV(j) has landed in O
-          tc_fence_after();
-          const float alpha = ex2_approx(m_used - m_new);
-          m_used = m_new;
-          // this thread rescales its half of the accumulator columns: h=0 -> [0,48), h=1 -> [48,96) and the denominator
-          uint32_t o32[32], o16[16];
-          tmem_ld32(tO + (h ? 64 : 0), o32);
-          tmem_ld16(tO + (h ? 48 : 32), o16);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o32[e] = __float_as_uint(__uint_as_float(o32[e]) * alpha);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) o16[e] = __float_as_uint(__uint_as_float(o16[e]) * alpha);
-          tmem_st32(tO + (h ? 64 : 0), o32);
-          tmem_st16(tO + (h ? 48 : 32), o16);
-          if (h) {
-            tmem_ld16(tO + 96, o16);                  // column 96 = running denominator (97..111 are zero)
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o16[e] = __float_as_uint(__uint_as_float(o16[e]) * alpha);
-            tmem_st16(tO + 96, o16);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        }
       }
-      // ---- epilogue: O / l (+ q) -> out[b, row, head*96 + 48h .. 48h+48)
+      // ---- epilogue: O / l (+ q) -> out[b, row, head*96 + :]
       mbar_wait(&o_done[i], (nkv - 1) & 1);
       tc_fence_after();
-      uint32_t o32[32], o16[16], od[16];
-      tmem_ld32(tO + (h ? 64 : 0), o32);
-      tmem_ld16(tO + (h ? 48 : 32), o16);
-      tmem_ld16(tO + 96, od);
-      tmem_ld_wait();
-      const float l_run = __uint_as_float(od[0]);
-      const float inv = 1.0f / l_run;
-      const int bb = bh / p.heads, head = bh % p.heads;
-      if (row < p.Lq) {
-        const bf16 *qrow = p.q + ((int64_t)bh * p.Lq + row) * D + h * 48;
-        bf16 *orow = p.out + (((int64_t)bb * p.Lq + row) * p.heads + head) * D + h * 48;
-        // channel order inside this thread's 48: h=0: o32 = ch 0..31, o16 = ch 32..47; h=1: o16 = ch 48..63, o32 = ch 64..95
-#pragma unroll
-        for (int v6 = 0; v6 < 6; ++v6) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ch = v6 * 8 + e;                // 0..47 within this half
-            uint32_t raw;
-            if (h == 0) raw = ch < 32 ? o32[ch] : o16[ch - 32];
-            else raw = ch < 16 ? o16[ch] : o32[ch - 16];
-            f[e] = __uint_as_float(raw) * inv;
-          }
-          uint4 qv = make_uint4(0, 0, 0, 0);
-          if (p.add_q) qv = *reinterpret_cast<const uint4 *>(qrow + v6 * 8);
-          const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = f[2 * e] + __uint_as_float(qw[e] << 16);
-            const float hi = f[2 * e + 1] + __uint_as_float(qw[e] & 0xffff0000u);
-            __nv_bfloat162 hh = __floats2bfloat162_rn(lo, hi);
-            w[e] = *reinterpret_cast<uint32_t *>(&hh);
-          }
-          *reinterpret_cast<uint4 *>(orow + v6 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        if (p.lse && h == 0) p.lse[(int64_t)bh * p.Lq + row] = (m_used + log2f(l_run)) * 0.69314718055994530942f;
+      float l_run;
+      {
+        uint32_t o[16];
+        tmem_ld16(tO + 96, o);
+        tmem_ld_wait();
+        l_run = __uint_as_float(o[0]);
       }
+      const float inv = 1.0f / l_run;
+      const int b = bh / p.heads, head = bh % p.heads;
+      const bool live = row < p.Lq;
+      const bf16 *qrow = p.q + ((int64_t)bh * p.Lq + row) * D;
+      bf16 *orow = p.out + (((int64_t)b * p.Lq + row) * p.heads + head) * D;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint32_t w[4];
+            uint4 qv = make_uint4(0, 0, 0, 0);
+            if (p.add_q) qv = *reinterpret_cast<const uint4 *>(qrow + c * 32 + v4 * 8);
+            const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float lo = __uint_as_float(o[v4 * 8 + 2 * e]) * inv;
+              float hi = __uint_as_float(o[v4 * 8 + 2 * e + 1]) * inv;
+              lo += __uint_as_float(qw[e] << 16);
+              hi += __uint_as_float(qw[e] & 0xffff0000u);
+              __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+              w[e] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            *reinterpret_cast<uint4 *>(orow + c * 32 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      if (p.lse && live) p.lse[(int64_t)bh * p.Lq + row] = (m_used + log2f(l_run)) * 0.69314718055994530942f;
     }
   }
   tc_fence_before();
@@ -377,16 +379,21 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
   if ((r = enc(&tq, a.q, a.Lq, attn::BQ))) return r;
   if ((r = enc(&tk, a.k, a.Lk, attn::BKV))) return r;
   if ((r = enc(&tv, a.v, a.Lk, attn::BKV))) return r;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      attn::kSmemBytes));
-    attr_done = true;
+  static int poly = -1;
+  if (poly < 0) {
+    const char *e = getenv("MVIT_ATTN_POLY");      // tuning knob; default: a quarter of the exponentials on the FMA pipe
+    poly = e ? atoi(e) : 1;
+    if (poly < 0 || poly > 2) poly = 1;
+    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
+    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
+    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
   }
   attn::Params p{static_cast<const bf16 *>(a.q), static_cast<bf16 *>(a.out), a.lse, a.heads, a.Lq, a.Lk, a.add_q,
                  a.scale * 1.44269504088896340736f};
   dim3 grid((unsigned)((a.Lq + 2 * attn::BQ - 1) / (2 * attn::BQ)), (unsigned)BH);
-  attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
+  if (poly == 0) attn::attention_tc_kernel<0><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
+  else if (poly == 2) attn::attention_tc_kernel<2><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
+  else attn::attention_tc_kernel<1><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
   MVIT_LAUNCH_OK("attention(tcgen05)");
   return 0;
 }
