@@ -112,15 +112,23 @@ __global__ void __launch_bounds__(256) im2col3d_kernel(const T *__restrict__ x, 
     }
   }
   __syncthreads();
+  // one thread = 8 columns of one patch row; a CTA covers blockDim.x / vpt consecutive tokens (vpt = vectors per
+  // token rounded up to a power of two) so the token decode is a handful of 32-bit operations per thread
   const int vecs = Kp / 8;
-  const int64_t total = (int64_t)B * To * Ho * Wo * vecs;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int vpt = 1;
+  while (vpt < vecs) vpt <<= 1;
+  const int tok_per_cta = blockDim.x / vpt;
+  const int v = threadIdx.x & (vpt - 1);
+  const int64_t n_tok = (int64_t)B * To * Ho * Wo;
   const int64_t clip_elems = (int64_t)C * Ti * H * W;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int v = (int)(i % vecs);
-    const int64_t m = i / vecs;
-    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), to = (int)((m / ((int64_t)Wo * Ho)) % To);
-    const int b = (int)(m / ((int64_t)Wo * Ho * To));
+  for (int64_t m = (int64_t)blockIdx.x * tok_per_cta + threadIdx.x / vpt; m < n_tok; m += (int64_t)gridDim.x * tok_per_cta) {
+    if (v >= vecs) continue;
+    const int per_clip = To * Ho * Wo;
+    const int b = (int)(m / per_clip);
+    int r = (int)(m - (int64_t)b * per_clip);
+    const int wo = r % Wo; r /= Wo;
+    const int ho = r % Ho;
+    const int to = r / Ho;
     const int t0 = to * st - pt, h0 = ho * sh - ph, w0 = wo * sw - pw;
     const T *base = x + b * clip_elems + ((int64_t)t0 * H + h0) * W + w0;     // may point before the clip: only
     const bool inside = t0 >= 0 && t0 + kt <= Ti && h0 >= 0 && h0 + kh <= H && w0 >= 0 && w0 + kw <= W;   // offset it
@@ -231,8 +239,12 @@ extern "C" int mvit_im2col3d_fwd(const void *clip, void *patches, int B, int C, 
   const int To = (T + 2 * pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
   MVIT_REQUIRE(To > 0 && Ho > 0 && Wo > 0, "im2col3d: empty output");
   if (B == 0) return 0;
-  const int64_t total = (int64_t)B * To * Ho * Wo * (Kp / 8);
-  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  int vpt = 1;
+  while (vpt < Kp / 8) vpt <<= 1;
+  MVIT_REQUIRE(vpt <= 256, "im2col3d: Kp too large");
+  const int64_t n_tok = (int64_t)B * To * Ho * Wo;
+  const int tok_per_cta = 256 / vpt;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n_tok + tok_per_cta - 1) / tok_per_cta, (int64_t)num_sms() * 64);
   const size_t smem = (size_t)Kp * sizeof(int2);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MVIT_F32)
