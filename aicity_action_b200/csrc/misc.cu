@@ -94,54 +94,56 @@ __global__ void preprocess_u8_kernel(const uint8_t *__restrict__ in, T *__restri
 }
 
 
-// im2col for Conv3d.  A CTA produces the patch rows of WS consecutive output tokens of one (b, to, ho) line:
-// the C*kt*kh input row segments those tokens touch are staged in shared memory with coalesced loads (zero-filled
-// outside the clip, so the inner loop has no border tests), then every thread assembles 8 consecutive columns of a
-// patch row (one 16-byte store for bf16) from shared memory.  Column k = ((c*kt + a)*kh + b)*kw + d.
-constexpr int kIm2colWS = 28;
+// im2col for Conv3d.  One thread produces 8 consecutive columns of one patch row (a single 16-byte store for
+// bf16, two for fp32).  Column k -> (c, a, b, d) is decoded once per CTA into a shared-memory table holding the
+// element offset inside a [C, T, H, W] clip and the (a, b, d) tap coordinates for the border test.
 template <typename T>
 __global__ void __launch_bounds__(256) im2col3d_kernel(const T *__restrict__ x, T *__restrict__ out, int B, int C, int Ti,
                                                        int H, int W, int kt, int kh, int kw, int st, int sh, int sw,
-                                                       int pt, int ph, int pw, int To, int Ho, int Wo, int Kp, int strips) {
-  extern __shared__ __align__(16) uint8_t im2col_smem[];
-  const int rows = C * kt * kh;                       // staged row segments
-  const int RL = (kIm2colWS - 1) * sw + kw;           // elements per staged segment
-  T *stage = reinterpret_cast<T *>(im2col_smem);      // [rows][RL]
-  const int kreal = rows * kw;
-  int bid = blockIdx.x;
-  const int strip = bid % strips; bid /= strips;
-  const int ho = bid % Ho; bid /= Ho;
-  const int to = bid % To;
-  const int b = bid / To;
-  const int wo0 = strip * kIm2colWS;
-  const int t0 = to * st - pt, h0 = ho * sh - ph, w0 = wo0 * sw - pw;
-  for (int i = threadIdx.x; i < rows * RL; i += blockDim.x) {
-    const int r = i / RL, col = i - r * RL;
-    const int bq = r % kh, a = (r / kh) % kt, c = r / (kh * kt);
-    const int t = t0 + a, h = h0 + bq, w = w0 + col;
-    T v = from_f32<T>(0.f);
-    if (t >= 0 && t < Ti && h >= 0 && h < H && w >= 0 && w < W) v = x[((((int64_t)b * C + c) * Ti + t) * H + h) * W + w];
-    stage[i] = v;
+                                                       int pt, int ph, int pw, int To, int Ho, int Wo, int Kp) {
+  extern __shared__ int2 lut[];                 // [Kp]: .x = element offset (or -1 for padding columns), .y = a | b<<8 | d<<16
+  const int kreal = C * kt * kh * kw;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    if (k < kreal) {
+      const int d = k % kw, bq = (k / kw) % kh, a = (k / (kw * kh)) % kt, c = k / (kw * kh * kt);
+      lut[k] = make_int2(((c * Ti + a) * H + bq) * W + d, a | (bq << 8) | (d << 16));
+    } else {
+      lut[k] = make_int2(-1, 0);
+    }
   }
   __syncthreads();
+  // one thread = 8 columns of one patch row; a CTA covers blockDim.x / vpt consecutive tokens (vpt = vectors per
+  // token rounded up to a power of two) so the token decode is a handful of 32-bit operations per thread
   const int vecs = Kp / 8;
   int vpt = 1;
   while (vpt < vecs) vpt <<= 1;
+  const int tok_per_cta = blockDim.x / vpt;
   const int v = threadIdx.x & (vpt - 1);
-  if (v >= vecs) return;
-  int lut[8];                                         // staged-element offset of this thread's 8 columns (-1: pad column)
+  const int64_t n_tok = (int64_t)B * To * Ho * Wo;
+  const int64_t clip_elems = (int64_t)C * Ti * H * W;
+  for (int64_t m = (int64_t)blockIdx.x * tok_per_cta + threadIdx.x / vpt; m < n_tok; m += (int64_t)gridDim.x * tok_per_cta) {
+    if (v >= vecs) continue;
+    const int per_clip = To * Ho * Wo;
+    const int b = (int)(m / per_clip);
+    int r = (int)(m - (int64_t)b * per_clip);
+    const int wo = r % Wo; r /= Wo;
+    const int ho = r % Ho;
+    const int to = r / Ho;
+    const int t0 = to * st - pt, h0 = ho * sh - ph, w0 = wo * sw - pw;
+    const T *base = x + b * clip_elems + ((int64_t)t0 * H + h0) * W + w0;     // may point before the clip: only
+    const bool inside = t0 >= 0 && t0 + kt <= Ti && h0 >= 0 && h0 + kh <= H && w0 >= 0 && w0 + kw <= W;   // offset it
+    T vals[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = v * 8 + e;
-    lut[e] = k < kreal ? (k / kw) * RL + (k % kw) : -1;
-  }
-  const int ntok = min(kIm2colWS, Wo - wo0);
-  const int64_t m0 = (((int64_t)b * To + to) * Ho + ho) * Wo + wo0;
-  for (int tk = threadIdx.x / vpt; tk < ntok; tk += blockDim.x / vpt) {
-    alignas(16) T vals[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) vals[e] = lut[e] >= 0 ? stage[lut[e] + tk * sw] : from_f32<T>(0.f);
-    T *dst = out + (m0 + tk) * Kp + v * 8;
+    for (int e = 0; e < 8; ++e) {
+      const int2 l = lut[v * 8 + e];
+      bool ok = l.x >= 0;
+      if (!inside && ok) {
+        const int t = t0 + (l.y & 0xff), h = h0 + ((l.y >> 8) & 0xff), w = w0 + (l.y >> 16);
+        ok = t >= 0 && t < Ti && h >= 0 && h < H && w >= 0 && w < W;
+      }
+      vals[e] = ok ? base[l.x] : from_f32<T>(0.f);
+    }
+    T *dst = out + m * Kp + v * 8;
     if constexpr (sizeof(T) == 2) {
       *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(vals);
     } else {
@@ -240,18 +242,15 @@ extern "C" int mvit_im2col3d_fwd(const void *clip, void *patches, int B, int C, 
   int vpt = 1;
   while (vpt < Kp / 8) vpt <<= 1;
   MVIT_REQUIRE(vpt <= 256, "im2col3d: Kp too large");
-  const int strips = (Wo + kIm2colWS - 1) / kIm2colWS;
-  const int64_t blocks64 = (int64_t)B * To * Ho * strips;
-  MVIT_REQUIRE(blocks64 < ((int64_t)1 << 31), "im2col3d: grid too large");
-  const unsigned blocks = (unsigned)blocks64;
-  const size_t esz = dtype == MVIT_BF16 ? 2 : 4;
-  const size_t smem = (size_t)C * kt * kh * ((kIm2colWS - 1) * sw + kw) * esz;
-  MVIT_REQUIRE(smem <= 48 * 1024, "im2col3d: staging tile too large");
+  const int64_t n_tok = (int64_t)B * To * Ho * Wo;
+  const int tok_per_cta = 256 / vpt;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n_tok + tok_per_cta - 1) / tok_per_cta, (int64_t)num_sms() * 64);
+  const size_t smem = (size_t)Kp * sizeof(int2);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MVIT_F32)
-    im2col3d_kernel<float><<<blocks, 256, smem, s>>>(static_cast<const float *>(clip), static_cast<float *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp, strips);
+    im2col3d_kernel<float><<<blocks, 256, smem, s>>>(static_cast<const float *>(clip), static_cast<float *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
   else if (dtype == MVIT_BF16)
-    im2col3d_kernel<bf16><<<blocks, 256, smem, s>>>(static_cast<const bf16 *>(clip), static_cast<bf16 *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp, strips);
+    im2col3d_kernel<bf16><<<blocks, 256, smem, s>>>(static_cast<const bf16 *>(clip), static_cast<bf16 *>(patches), B, C, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kp);
   else MVIT_REQUIRE(false, "im2col3d: unknown dtype");
   MVIT_LAUNCH_OK("im2col3d");
   return 0;
