@@ -34,6 +34,8 @@ SIGNATURES = {
     "mvit_pos_embed_add": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mvit_mean_head_workspace_floats": (C.c_size_t, [_i, _i, _i]),
     "mvit_mean_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mvit_fold_clip_fwd": (_i, [_p, _i, _p] + [_i] * 9 + [_f, _f, _p]),
+    "mvit_patch_conv_fwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 12 + [_p]),
     "mvit_preprocess_u8_fwd": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _p]),
 }
 

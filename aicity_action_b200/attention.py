@@ -26,7 +26,7 @@ from .weights import cached_weight
 def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     """fp32 tensors run the fp32 kernels unless a bf16 autocast region is active (the reference's
     TRAIN.MIXED_PRECISION / torch.autocast contract); bf16 tensors run the tensor-core kernels."""
-    if x.dtype == torch.bfloat16:
+    if x.dtype == torch.bfloat16 or x.dtype == torch.uint8:     # uint8 = raw frames, normalised on the device
         return torch.bfloat16
     if x.dtype == torch.float32:
         if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:

@@ -52,11 +52,28 @@ template <int BN, bool PAIR> struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
 };
 
+// Implicit-GEMM convolution mode (patch embedding): the A operand is a folded clip [B, Tf, Hf, Wf, Cf] read through a
+// 5-D tensor map; an M tile is an 8(w) x 8(h) x 2(t) patch of output tokens and k-block kb = (tap, 64-channel slice):
+// the TMA box of tap (dt, dh, dw) is the same patch shifted by the tap offset, zero-filled outside the clip.
+struct ConvGeom {
+  int enabled, Tf, Hf, Wf, cblocks, nt, nh, nw, lo_t, lo_h, lo_w;
+};
 struct Params {
   const float *bias, *row_scale;
   int64_t M, rows_per_sample, res_period;
   int N, K, epilogue, has_residual;
+  ConvGeom conv;
 };
+struct TileCoord { int b, t0, h0, w0; };
+__device__ __forceinline__ TileCoord conv_tile(const ConvGeom &g, int64_t mt) {
+  TileCoord c;
+  const int wq = g.Wf / 8, hq = g.Hf / 8, tq = g.Tf / 2;
+  c.w0 = (int)(mt % wq) * 8; mt /= wq;
+  c.h0 = (int)(mt % hq) * 8; mt /= hq;
+  c.t0 = (int)(mt % tq) * 2;
+  c.b = (int)(mt / tq);
+  return c;
+}
 
 // GELU(x) = x * (0.5 + phi(x)),  phi(x) = 0.5*erf(x/sqrt2) ~ xc * P(xc^2) with xc = clamp(x, -4, 4) (degree-7 minimax
 // fit: |gelu error| < 9e-5 on [-4, 4] and < 5e-5*|x| outside, far below bf16 resolution).  FMA pipe only (no MUFU),
@@ -154,7 +171,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tma_load_2d_pair(sB + stage * C::kBBytes, &tmap_w, &full[stage], kb * BK, n0 + (int)rank * C::kBRows);
           } else {
             mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-            tma_load_2d(sA + stage * C::kABytes, &tmap_x, &full[stage], kb * BK, m0);
+            if (p.conv.enabled) {
+              const TileCoord tc = conv_tile(p.conv, t / n_tiles);
+              const int tap = kb / p.conv.cblocks, kc = kb - tap * p.conv.cblocks;
+              const int dw = p.conv.lo_w + tap % p.conv.nw, dh = p.conv.lo_h + (tap / p.conv.nw) % p.conv.nh,
+                        dt = p.conv.lo_t + tap / (p.conv.nw * p.conv.nh);
+              tma_load_5d(sA + stage * C::kABytes, &tmap_x, &full[stage], kc * BK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.b);
+            } else {
+              tma_load_2d(sA + stage * C::kABytes, &tmap_x, &full[stage], kb * BK, m0);
+            }
             tma_load_2d(sB + stage * C::kBBytes, &tmap_w, &full[stage], kb * BK, n0);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -205,9 +230,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const int64_t mrow = (t / n_tiles) * TM + rank * BM;
           const int m0 = (int)(p.res_period ? mrow % p.res_period : mrow), n0 = (int)(t % n_tiles) * BN;
           mbar_arrive_expect_tx(&res_full[buf], C::kOutBytes);
+          if (p.conv.enabled) {                         // positional table [Tf, Hf, Wf, N], same patch, no batch axis
+            const TileCoord tc = conv_tile(p.conv, t / n_tiles);
 #pragma unroll
-          for (int bx = 0; bx < C::kBoxes; ++bx)
-            tma_load_2d(sOut + buf * C::kOutBytes + bx * kBoxBytes, &tmap_r, &res_full[buf], n0 + bx * kBoxCols, m0);
+            for (int bx = 0; bx < C::kBoxes; ++bx)
+              tma_load_4d(sOut + buf * C::kOutBytes + bx * kBoxBytes, &tmap_r, &res_full[buf], n0 + bx * kBoxCols, tc.w0,
+                          tc.h0, tc.t0);
+          } else {
+#pragma unroll
+            for (int bx = 0; bx < C::kBoxes; ++bx)
+              tma_load_2d(sOut + buf * C::kOutBytes + bx * kBoxBytes, &tmap_r, &res_full[buf], n0 + bx * kBoxCols, m0);
+          }
         } else {
           mbar_arrive(&res_full[buf]);
         }
@@ -308,9 +341,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (et == 0) {
+        if (p.conv.enabled) {
+          const TileCoord tc = conv_tile(p.conv, t / n_tiles);
 #pragma unroll
-        for (int bx = 0; bx < C::kBoxes; ++bx)
-          if (n0 + bx * kBoxCols < p.N) tma_store_2d(&tmap_y, obuf + bx * kBoxBytes, n0 + bx * kBoxCols, (int)m0);
+          for (int bx = 0; bx < C::kBoxes; ++bx)
+            if (n0 + bx * kBoxCols < p.N)
+              tma_store_5d(&tmap_y, obuf + bx * kBoxBytes, n0 + bx * kBoxCols, tc.w0, tc.h0, tc.t0, tc.b);
+        } else {
+#pragma unroll
+          for (int bx = 0; bx < C::kBoxes; ++bx)
+            if (n0 + bx * kBoxCols < p.N) tma_store_2d(&tmap_y, obuf + bx * kBoxBytes, n0 + bx * kBoxCols, (int)m0);
+        }
         tma_store_commit();
         if (it > 0) {
           tma_store_wait_read<1>();                    // the previous tile's store has drained its buffer
@@ -404,7 +445,7 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
     MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
-  gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0};
+  gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0, {}};
   constexpr int TM = PAIR ? 2 * gemm::BM : gemm::BM;
   const int64_t tiles = ((a.M + TM - 1) / TM) * ((a.N + BN - 1) / BN);
   cudaLaunchConfig_t cfg{};
@@ -424,6 +465,55 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   MVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm::linear_tc_kernel<BN, PAIR>, tx, tw, ty, tr, p));
+  return 0;
+}
+
+// Patch-embedding convolution as an implicit GEMM over the folded clip (see ConvGeom).  M = B*Tf*Hf*Wf tokens,
+// K = taps * Cf, N = Cout; tile = <96, false>.
+int patch_conv_tc(const void *folded, const void *wf, const float *bias, const void *pos, void *out, int B, int Tf,
+                  int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N, cudaStream_t st) {
+  using C = gemm::Cfg<96, false>;
+  MVIT_REQUIRE(Tf % 2 == 0 && Hf % 8 == 0 && Wf % 8 == 0, "patch_conv: token grid must be a multiple of 2x8x8");
+  MVIT_REQUIRE(Cf % gemm::BK == 0 && N % 8 == 0, "patch_conv: folded channels must be a multiple of 64, Cout of 8");
+  CUtensorMap tx, tw, ty, tr;
+  int r;
+  {
+    const uint64_t dims[5] = {(uint64_t)Cf, (uint64_t)Wf, (uint64_t)Hf, (uint64_t)Tf, (uint64_t)B};
+    const uint64_t str[4] = {(uint64_t)Cf * 2, (uint64_t)Wf * Cf * 2, (uint64_t)Hf * Wf * Cf * 2, (uint64_t)Tf * Hf * Wf * Cf * 2};
+    const uint32_t box[5] = {gemm::BK, 8, 8, 2, 1};
+    if ((r = encode_tmap_bf16(&tx, folded, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  }
+  const int K = nt * nh * nw * Cf;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {gemm::BK, 96};
+    if ((r = encode_tmap_bf16(&tw, wf, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  }
+  {
+    const uint64_t dims[5] = {(uint64_t)N, (uint64_t)Wf, (uint64_t)Hf, (uint64_t)Tf, (uint64_t)B};
+    const uint64_t str[4] = {(uint64_t)N * 2, (uint64_t)Wf * N * 2, (uint64_t)Hf * Wf * N * 2, (uint64_t)Tf * Hf * Wf * N * 2};
+    const uint32_t box[5] = {gemm::kBoxCols, 8, 8, 2, 1};
+    if ((r = encode_tmap_bf16(&ty, out, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+    if (pos) {
+      const uint32_t box4[4] = {gemm::kBoxCols, 8, 8, 2};
+      if ((r = encode_tmap_bf16(&tr, pos, 4, dims, str, box4, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+    } else {
+      tr = ty;
+    }
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  const int64_t M = (int64_t)B * Tf * Hf * Wf;
+  gemm::Params p{bias, nullptr, M, 0, 0, N, K, MVIT_EPI_NONE, pos ? 1 : 0,
+                 {1, Tf, Hf, Wf, Cf / gemm::BK, nt, nh, nw, lo_t, lo_h, lo_w}};
+  const int64_t tiles = (M / gemm::BM) * ((N + 95) / 96);
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
+  gemm::linear_tc_kernel<96, false><<<grid, gemm::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+  MVIT_LAUNCH_OK("patch_conv(tcgen05)");
   return 0;
 }
 

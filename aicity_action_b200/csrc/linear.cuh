@@ -16,5 +16,7 @@ int linear_simt(const LinearArgs &a, int dtype, cudaStream_t st);
 // tcgen05 path (gemm_tc.cu), bf16 only
 int linear_tc(const LinearArgs &a, cudaStream_t st);
 bool linear_tc_supported(const LinearArgs &a, const char **why);
+int patch_conv_tc(const void *folded, const void *wf, const float *bias, const void *pos, void *out, int B, int Tf,
+                  int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N, cudaStream_t st);
 
 }  // namespace mvit

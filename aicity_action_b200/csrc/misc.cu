@@ -1,5 +1,5 @@
 // Small memory-bound kernels around the block stack: positional-embedding add and mean-pool + head.
-#include "common.cuh"
+#include "linear.cuh"
 
 namespace mvit {
 
@@ -153,6 +153,63 @@ __global__ void __launch_bounds__(256) im2col3d_kernel(const T *__restrict__ x, 
   }
 }
 
+
+// Space-to-depth "fold" of a clip for the implicit-GEMM patch embedding (gemm_tc.cu, ConvGeom): the conv stride
+// (st, sh, sw) is folded into channels,  folded[b, t/st, h/sh, w/sw, ((t%st*sh + h%sh)*sw + w%sw)*C + c] = x[b,c,t,h,w]
+// (channels [st*sh*sw*C, Cf) are zero padding).  A CTA handles 16 consecutive output tokens of one (b, tf, hf) line:
+// coalesced row loads into shared memory, coalesced 2*Cf-byte token stores.  SRC = float / bf16 channels-first clip, or
+// uint8 channels-last frames with the reference normalisation ((x/255 - mean)/std, module_wrapper.py:332-346) fused in.
+constexpr int kFoldTok = 16;
+template <typename SRC, bool FRAMES_U8>
+__global__ void __launch_bounds__(256) fold_clip_kernel(const SRC *__restrict__ x, bf16 *__restrict__ out, int B, int C, int T,
+                                                        int H, int W, int st, int sh, int sw, int Cf, float mean, float stdv,
+                                                        int strips) {
+  extern __shared__ __align__(16) uint8_t fold_smem[];
+  SRC *stage = reinterpret_cast<SRC *>(fold_smem);
+  const int Tf = T / st, Hf = H / sh, Wf = W / sw;
+  int bid = blockIdx.x;
+  const int strip = bid % strips; bid /= strips;
+  const int hf = bid % Hf; bid /= Hf;
+  const int tf = bid % Tf;
+  const int b = bid / Tf;
+  const int wf0 = strip * kFoldTok;
+  const int ntok = min(kFoldTok, Wf - wf0);
+  const int RL = kFoldTok * sw * (FRAMES_U8 ? C : 1);          // staged elements per row
+  const int rows = FRAMES_U8 ? st * sh : C * st * sh;
+  for (int i = threadIdx.x; i < rows * RL; i += blockDim.x) {
+    const int r = i / RL, col = i - r * RL;
+    SRC v = SRC(0);
+    if (FRAMES_U8) {                                           // row r = (ot, oh); col = (w_local, c)
+      const int oh = r % sh, ot = r / sh;
+      const int wl = col / C;
+      if (wl < ntok * sw)
+        v = x[((((int64_t)b * T + tf * st + ot) * H + hf * sh + oh) * W + wf0 * sw) * C + col];
+    } else {                                                   // row r = (c, ot, oh); col = w_local
+      const int oh = r % sh, ot = (r / sh) % st, c = r / (sh * st);
+      if (col < ntok * sw)
+        v = x[((((int64_t)b * C + c) * T + tf * st + ot) * H + hf * sh + oh) * W + wf0 * sw + col];
+    }
+    stage[i] = v;
+  }
+  __syncthreads();
+  const int creal = st * sh * sw * C;
+  bf16 *dst = out + ((((int64_t)b * Tf + tf) * Hf + hf) * Wf + wf0) * Cf;
+  for (int i = threadIdx.x; i < ntok * Cf; i += blockDim.x) {
+    const int tk = i / Cf, ch = i - tk * Cf;
+    float v = 0.f;
+    if (ch < creal) {
+      const int c = ch % C, ow = (ch / C) % sw, oh = (ch / (C * sw)) % sh, ot = ch / (C * sw * sh);
+      if (FRAMES_U8) {
+        const float raw = (float)stage[(ot * sh + oh) * RL + (tk * sw + ow) * C + c];
+        v = __fdiv_rn(__fsub_rn(__fdiv_rn(raw, 255.0f), mean), stdv);
+      } else {
+        v = to_f32(stage[((c * st + ot) * sh + oh) * RL + tk * sw + ow]);
+      }
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace mvit
 
 extern "C" int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
@@ -254,4 +311,42 @@ extern "C" int mvit_im2col3d_fwd(const void *clip, void *patches, int B, int C, 
   else MVIT_REQUIRE(false, "im2col3d: unknown dtype");
   MVIT_LAUNCH_OK("im2col3d");
   return 0;
+}
+
+extern "C" int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, int B, int C, int T, int H, int W,
+                                  int st, int sh, int sw, int Cf, float mean, float stdv, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(clip && folded, "fold_clip: null pointer");
+  MVIT_REQUIRE(B >= 0 && C > 0 && st > 0 && sh > 0 && sw > 0 && T % st == 0 && H % sh == 0 && W % sw == 0,
+               "fold_clip: clip size must be a multiple of the stride");
+  MVIT_REQUIRE(Cf >= st * sh * sw * C, "fold_clip: Cf too small");
+  MVIT_REQUIRE(src_kind >= 0 && src_kind <= 2, "fold_clip: src_kind 0 = f32 [B,C,T,H,W], 1 = bf16 [B,C,T,H,W], 2 = u8 [B,T,H,W,C]");
+  if (B == 0) return 0;
+  const int Wf = W / sw, strips = (Wf + kFoldTok - 1) / kFoldTok;
+  const int64_t blocks = (int64_t)B * (T / st) * (H / sh) * strips;
+  MVIT_REQUIRE(blocks < ((int64_t)1 << 31), "fold_clip: grid too large");
+  const size_t esz = src_kind == 0 ? 4 : (src_kind == 1 ? 2 : 1);
+  const size_t smem = (size_t)C * st * sh * kFoldTok * sw * esz;
+  MVIT_REQUIRE(smem <= 48 * 1024, "fold_clip: staging tile too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bf16 *o = static_cast<bf16 *>(folded);
+  if (src_kind == 0)
+    fold_clip_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>(static_cast<const float *>(clip), o, B, C, T, H, W, st, sh, sw, Cf, mean, stdv, strips);
+  else if (src_kind == 1)
+    fold_clip_kernel<bf16, false><<<(unsigned)blocks, 256, smem, s>>>(static_cast<const bf16 *>(clip), o, B, C, T, H, W, st, sh, sw, Cf, mean, stdv, strips);
+  else
+    fold_clip_kernel<unsigned char, true><<<(unsigned)blocks, 256, smem, s>>>(static_cast<const unsigned char *>(clip), o, B, C, T, H, W, st, sh, sw, Cf, mean, stdv, strips);
+  MVIT_LAUNCH_OK("fold_clip");
+  return 0;
+}
+
+extern "C" int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out,
+                                   int B, int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h,
+                                   int lo_w, int N, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(folded && wf && out, "patch_conv: null pointer");
+  MVIT_REQUIRE(B >= 0 && Tf > 0 && Hf > 0 && Wf > 0 && nt > 0 && nh > 0 && nw > 0 && N > 0, "patch_conv: bad shape");
+  if (B == 0) return 0;
+  return patch_conv_tc(folded, wf, bias, pos, out, B, Tf, Hf, Wf, Cf, nt, nh, nw, lo_t, lo_h, lo_w, N,
+                       static_cast<cudaStream_t>(stream));
 }

@@ -59,13 +59,67 @@ class PatchEmbed(nn.Module):
             self._b200_w = slot
         return slot[1]
 
+    # ---- implicit-GEMM path (bf16): fold the stride into channels, then one tcgen05 GEMM over 5-D TMA tap boxes
+    def _fold_geometry(self):
+        k, s, p = list(self.proj.kernel_size), list(self.proj.stride), list(self.proj.padding)
+        lo = [-((pp + ss - 1) // ss) for pp, ss in zip(p, s)]                 # first folded block a window touches
+        hi = [(kk - 1 - pp) // ss for kk, pp, ss in zip(k, p, s)]
+        taps = [h - l + 1 for h, l in zip(hi, lo)]
+        creal = s[0] * s[1] * s[2] * self.proj.in_channels
+        return k, s, p, lo, taps, creal, (creal + 63) // 64 * 64
+
+    def _folded_weight(self):
+        """Conv3d weight scattered into the folded layout: [Cout, taps_t*taps_h*taps_w*Cf] bf16 (cached)."""
+        w = self.proj.weight
+        key = (w._version, w.device, w.data_ptr())
+        slot = getattr(self, "_b200_wf", None)
+        if slot is None or slot[0] != key:
+            k, s, p, lo, taps, creal, cf = self._fold_geometry()
+            C = self.proj.in_channels
+            wf = torch.zeros((w.shape[0], taps[0], taps[1], taps[2], cf), dtype=torch.float32, device=w.device)
+            wd = w.detach().float()
+            for a in range(k[0]):
+                bt, ot = divmod(a - p[0], s[0])                # folded block (relative to the output index), offset in block
+                for b in range(k[1]):
+                    bh, oh = divmod(b - p[1], s[1])
+                    for d in range(k[2]):
+                        bw, ow = divmod(d - p[2], s[2])
+                        ch = ((ot * s[1] + oh) * s[2] + ow) * C
+                        wf[:, bt - lo[0], bh - lo[1], bw - lo[2], ch:ch + C] = wd[:, :, a, b, d]
+            slot = (key, wf.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous())
+            self._b200_wf = slot
+        return slot[1]
+
+    def _conv_path_ok(self, x, dtype):
+        if self.conv_2d or dtype != torch.bfloat16:
+            return False
+        if x.dtype == torch.uint8:
+            T, H, W = x.shape[1:4]
+        else:
+            T, H, W = x.shape[2:5]
+        s = self.proj.stride
+        if T % s[0] or H % s[1] or W % s[2]:
+            return False
+        k, _, p, _, _, _, _ = self._fold_geometry()
+        out = [(n + 2 * pp - kk) // ss + 1 for n, kk, ss, pp in zip((T, H, W), k, s, p)]
+        if out != [T // s[0], H // s[1], W // s[2]]:
+            return False
+        return out[0] % 2 == 0 and out[1] % 8 == 0 and out[2] % 8 == 0 and self.proj.out_channels % 8 == 0
+
     def forward(self, x, dtype=None, pos=None, pos_period=0):
-        """x: [B, C, T, H, W] (or [B, C, H, W] for conv_2d) -> tokens [B, L, Cout].
-        The convolution runs as im2col + one GEMM (tensor cores for bf16); `pos` ([pos_period, Cout] table
-        in the activation dtype) is added in the GEMM epilogue together with the bias."""
+        """x: [B, C, T, H, W] clip (or [B, C, H, W] for conv_2d; or uint8 frames [B, T, H, W, C], normalised on the
+        fly) -> tokens [B, L, Cout].  bf16: space-to-depth fold + implicit-GEMM convolution on tensor cores (5-D TMA,
+        no im2col matrix); otherwise im2col + GEMM.  `pos` ([L, Cout] table in the activation dtype) and the bias are
+        added in the GEMM epilogue."""
         if not x.is_cuda:
             raise ops._lib.MvitLibraryError("aicity_action_b200 runs on CUDA tensors only (no CPU fallback)")
-        dtype = dtype or x.dtype
+        dtype = dtype or (torch.bfloat16 if x.dtype == torch.uint8 else x.dtype)
+        if self._conv_path_ok(x, dtype):
+            _, s, _, lo, taps, _, cf = self._fold_geometry()
+            folded = ops.fold_clip(x, s, cf)
+            return ops.patch_conv(folded, self._folded_weight(), self.proj.bias, pos, taps, lo)
+        if x.dtype == torch.uint8:
+            x = ops.preprocess_u8(x, dtype)
         t3 = lambda v: [1] + list(v) if self.conv_2d else list(v)
         if self.conv_2d:
             x = x.unsqueeze(2)

@@ -269,3 +269,44 @@ def im2col3d(clip: torch.Tensor, kernel: Sequence[int], stride: Sequence[int], p
                                             _dt(clip), _stream()), "mvit_im2col3d_fwd")
     launch_count += 1
     return out, [To, Ho, Wo]
+
+
+def fold_clip(clip: torch.Tensor, stride: Sequence[int], Cf: int, mean: float = 0.45, std: float = 0.225) -> torch.Tensor:
+    """Space-to-depth of a clip by the patch-embed stride (see mvit_fold_clip_fwd).  `clip` is a channels-first
+    fp32/bf16 clip [B, C, T, H, W] or uint8 frames [B, T, H, W, C] (normalised on the fly); returns bf16
+    [B, T/st, H/sh, W/sw, Cf]."""
+    global launch_count
+    _need_cuda(clip)
+    clip = clip.contiguous()
+    if clip.dtype == torch.uint8:
+        B, T, H, W, Cc = clip.shape
+        kind = 2
+    else:
+        B, Cc, T, H, W = clip.shape
+        kind = {torch.float32: 0, torch.bfloat16: 1}[clip.dtype]
+    st, sh, sw = stride
+    out = torch.empty((B, T // st, H // sh, W // sw, Cf), dtype=torch.bfloat16, device=clip.device)
+    with _Timed("fold_clip", float(clip.numel() * clip.element_size() + out.numel() * 2)):
+        check(_lib.load().mvit_fold_clip_fwd(_ptr(clip), kind, _ptr(out), B, Cc, T, H, W, st, sh, sw, Cf, float(mean),
+                                             float(std), _stream()), "mvit_fold_clip_fwd")
+    launch_count += 1
+    return out
+
+
+def patch_conv(folded: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], pos: Optional[torch.Tensor],
+               taps: Sequence[int], lows: Sequence[int]) -> torch.Tensor:
+    """Implicit-GEMM patch embedding on the folded clip: returns tokens [B, Tf*Hf*Wf, N] (bf16)."""
+    global launch_count
+    _need_cuda(folded, wf, bias, pos)
+    B, Tf, Hf, Wf, Cf = folded.shape
+    N = wf.shape[0]
+    assert folded.dtype == torch.bfloat16 and wf.dtype == torch.bfloat16 and wf.is_contiguous()
+    assert wf.shape[1] == taps[0] * taps[1] * taps[2] * Cf
+    out = torch.empty((B, Tf * Hf * Wf, N), dtype=torch.bfloat16, device=folded.device)
+    bias = _f32c(bias)
+    with _Timed("patch_conv", 2.0 * B * Tf * Hf * Wf * N * wf.shape[1]):
+        check(_lib.load().mvit_patch_conv_fwd(_ptr(folded), _ptr(wf), _ptr(bias), _ptr(pos), _ptr(out), B, Tf, Hf, Wf, Cf,
+                                              taps[0], taps[1], taps[2], lows[0], lows[1], lows[2], N, _stream()),
+              "mvit_patch_conv_fwd")
+    launch_count += 1
+    return out

@@ -148,6 +148,24 @@ int mvit_mean_head_fwd(const void *x, const float *w, const float *bias, float *
 int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, int T, int H, int W, float mean,
                            float std, int dtype, void *stream);
 
+/*
+ * Patch embedding as an implicit GEMM (stem_helper.py:308-338 Conv3d + video_model_builder.py:1206-1223 pos-embed).
+ *  1. mvit_fold_clip_fwd: space-to-depth of the clip by the conv stride,
+ *       folded[b, t/st, h/sh, w/sw, ((t%st*sh + h%sh)*sw + w%sw)*C + c] = x[b, c, t, h, w]      (bf16, zero padded to Cf)
+ *     src_kind 0 / 1: fp32 / bf16 channels-first clip [B, C, T, H, W] (what the reference feeds the model);
+ *     src_kind 2: uint8 channels-last frames [B, T, H, W, C] with the reference normalisation (x/255 - mean)/std fused.
+ *  2. mvit_patch_conv_fwd: out[b, t, h, w, :] = sum_taps folded[b, t+dt, h+dh, w+dw, :] . wf[:, tap, :] + bias + pos[t,h,w,:]
+ *     on tcgen05 tensor cores; every tap's operand tile is fetched by a 5-D TMA box shifted by the tap offset
+ *     (zero fill outside the clip) - no im2col matrix exists.  wf: [N, nt*nh*nw*Cf] bf16 (the Conv3d weight scattered
+ *     into the folded layout by the host), taps dt in [lo_t, lo_t+nt) etc.; pos: [Tf, Hf, Wf, N] bf16 or NULL.
+ *     Requires Tf % 2 == 0, Hf % 8 == 0, Wf % 8 == 0, Cf % 64 == 0.
+ */
+int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, int B, int C, int T, int H, int W, int st,
+                       int sh, int sw, int Cf, float mean, float std, void *stream);
+int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out, int B,
+                        int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

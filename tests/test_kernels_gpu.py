@@ -187,3 +187,30 @@ def test_patch_embed_im2col_gemm(dtype):
     for impl in _impls(dtype):
         got = ops.linear(patches, dev(wp, dtype), dev(bias), residual=dev(pos, dtype), residual_row_period=N, impl=impl)
         assert rel_inf(got.view(B, N, 96), ref) < TOL[dtype], impl
+
+
+def test_patch_embed_implicit_gemm_conv():
+    """fold + tcgen05 implicit-GEMM convolution (5-D TMA tap boxes) == Conv3d + pos-embed; uint8 frames == clip."""
+    from aicity_action_b200.mvit import PatchEmbed
+    B, T, S = 2, 8, 64
+    pe = PatchEmbed(3, 96, (3, 7, 7), (2, 4, 4), (1, 3, 3))
+    with torch.no_grad():
+        pe.proj.weight.copy_(synth_input(7, "pw", (96, 3, 3, 7, 7)) / 21.0)
+        pe.proj.bias.copy_(synth_input(7, "pb", (96,)) * 0.1)
+    pe = pe.cuda()
+    g = torch.Generator().manual_seed(11)
+    frames = torch.randint(0, 256, (B, T, S, S, 3), dtype=torch.uint8, generator=g)
+    clip = ((frames.float() / 255.0 - 0.45) / 0.225).permute(0, 4, 1, 2, 3).contiguous()
+    xr = rounded(clip, torch.bfloat16)
+    wr = rounded(pe.proj.weight.detach().cpu(), torch.bfloat16)
+    ref = F.conv3d(xr, wr, pe.proj.bias.detach().cpu(), stride=(2, 4, 4), padding=(1, 3, 3)).flatten(2).transpose(1, 2)
+    N = ref.shape[1]
+    pos = rounded(synth_input(7, "pos", (N, 96)) * 0.1, torch.bfloat16)
+    with torch.no_grad():
+        got_clip = pe(xr.cuda().bfloat16(), torch.bfloat16, pos=pos.cuda().bfloat16(), pos_period=N)
+        got_u8 = pe(frames.cuda(), torch.bfloat16, pos=pos.cuda().bfloat16(), pos_period=N)
+        got_nopos = pe(xr.cuda().bfloat16(), torch.bfloat16)
+    assert got_clip.shape == (B, N, 96)
+    assert rel_inf(got_clip, ref + pos) < TOL[torch.bfloat16]
+    assert rel_inf(got_u8, ref + pos) < TOL[torch.bfloat16]
+    assert rel_inf(got_nopos, ref) < TOL[torch.bfloat16]
