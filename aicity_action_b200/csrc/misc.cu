@@ -210,6 +210,66 @@ __global__ void __launch_bounds__(256) fold_clip_kernel(const SRC *__restrict__ 
   }
 }
 
+
+// Specialisation of the fold for the MViT patch embedding (C = 3, stride (2,4,4), Cf = 128, bf16 / uint8 sources):
+// compile-time geometry, 16-byte staging loads, one 16-byte store (8 folded channels) per thread.
+// Folded channel ch = ((ot*4 + oh)*4 + ow)*3 + c.
+template <typename SRC, bool FRAMES_U8>
+__global__ void __launch_bounds__(256) fold_clip_244x3_kernel(const SRC *__restrict__ x, bf16 *__restrict__ out, int B, int T,
+                                                              int H, int W, float mean, float stdv, int strips) {
+  constexpr int C = 3, ST = 2, SH = 4, SW = 4, CF = 128, TOK = kFoldTok;
+  constexpr int ROWS = FRAMES_U8 ? ST * SH : C * ST * SH;          // 8 / 24 staged rows
+  constexpr int RL = TOK * SW * (FRAMES_U8 ? C : 1);               // 192 / 64 elements per row
+  constexpr int VEC = 16 / (int)sizeof(SRC);                       // elements per 16-byte staging vector
+  __shared__ __align__(16) SRC stage[ROWS * RL];
+  const int Tf = T / ST, Hf = H / SH, Wf = W / SW;
+  int bid = blockIdx.x;
+  const int strip = bid % strips; bid /= strips;
+  const int hf = bid % Hf; bid /= Hf;
+  const int tf = bid % Tf;
+  const int b = bid / Tf;
+  const int wf0 = strip * TOK;
+  const int ntok = min(TOK, Wf - wf0);
+  for (int i = threadIdx.x; i < ROWS * RL / VEC; i += 256) {
+    const int r = i / (RL / VEC), cv = (i % (RL / VEC)) * VEC;
+    const SRC *src;
+    int live_elems;
+    if (FRAMES_U8) {
+      const int oh = r % SH, ot = r / SH;
+      src = x + ((((int64_t)b * T + tf * ST + ot) * H + hf * SH + oh) * W + wf0 * SW) * C + cv;
+      live_elems = ntok * SW * C;
+    } else {
+      const int oh = r % SH, ot = (r / SH) % ST, c = r / (SH * ST);
+      src = x + ((((int64_t)b * C + c) * T + tf * ST + ot) * H + hf * SH + oh) * W + wf0 * SW + cv;
+      live_elems = ntok * SW;
+    }
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (cv + VEC <= live_elems) v = *reinterpret_cast<const uint4 *>(src);
+    *reinterpret_cast<uint4 *>(&stage[r * RL + cv]) = v;
+  }
+  __syncthreads();
+  const int tk = threadIdx.x >> 4, v8 = threadIdx.x & 15;          // token, group of 8 folded channels
+  if (tk >= ntok) return;
+  alignas(16) bf16 o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = v8 * 8 + e;
+    float val = 0.f;
+    if (ch < ST * SH * SW * C) {
+      const int c = ch % C, ow = (ch / C) % SW, oh = (ch / (C * SW)) % SH, ot = ch / (C * SW * SH);
+      if (FRAMES_U8) {
+        const float raw = (float)stage[(ot * SH + oh) * RL + (tk * SW + ow) * C + c];
+        val = __fdiv_rn(__fsub_rn(__fdiv_rn(raw, 255.0f), mean), stdv);
+      } else {
+        val = to_f32(stage[((c * ST + ot) * SH + oh) * RL + tk * SW + ow]);
+      }
+    }
+    o[e] = __float2bfloat16_rn(val);
+  }
+  bf16 *dst = out + ((((int64_t)b * Tf + tf) * Hf + hf) * Wf + wf0 + tk) * CF + v8 * 8;
+  *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(o);
+}
+
 }  // namespace mvit
 
 extern "C" int mvit_pos_embed_add(const void *src, int src_dtype, const float *pos_spatial,
@@ -330,6 +390,18 @@ extern "C" int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, 
   MVIT_REQUIRE(smem <= 48 * 1024, "fold_clip: staging tile too large");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bf16 *o = static_cast<bf16 *>(folded);
+  // tuned path: the MViT patch-embed geometry with 16-byte aligned rows
+  const bool fast = C == 3 && st == 2 && sh == 4 && sw == 4 && Cf == 128 && src_kind != 0 && Wf % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(clip) & 15) == 0 && (reinterpret_cast<uintptr_t>(folded) & 15) == 0 &&
+                    (src_kind == 2 ? (W * 3) % 16 == 0 : W % 8 == 0);
+  if (fast) {
+    if (src_kind == 1)
+      fold_clip_244x3_kernel<bf16, false><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const bf16 *>(clip), o, B, T, H, W, mean, stdv, strips);
+    else
+      fold_clip_244x3_kernel<unsigned char, true><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const unsigned char *>(clip), o, B, T, H, W, mean, stdv, strips);
+    MVIT_LAUNCH_OK("fold_clip(2,4,4)");
+    return 0;
+  }
   if (src_kind == 0)
     fold_clip_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>(static_cast<const float *>(clip), o, B, C, T, H, W, st, sh, sw, Cf, mean, stdv, strips);
   else if (src_kind == 1)
