@@ -35,6 +35,17 @@ def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     raise TypeError(f"unsupported activation dtype {x.dtype} (float32 or bfloat16)")
 
 
+_SIDE = {}
+
+
+def _side_streams(device):
+    """Two auxiliary CUDA streams per device for the K / V pooling launches."""
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _SIDE[key]
+
+
 def _no_grad_only(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
@@ -166,9 +177,25 @@ class MultiScaleAttention(nn.Module):
         C, h = self.dim_out, self.num_heads
         qkv = ops.linear(x, cached_weight(self.qkv.weight, x.dtype), self.qkv.bias)
         qkv5 = qkv.view(B, N, 3, h, C // h)
+        # the three pooling launches are independent: K and V run on side streams next to Q so the small
+        # deep-stage launches overlap instead of queueing (fork / join with events, graph-capturable)
+        cur = torch.cuda.current_stream()
+        side = _side_streams(x.device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs = [None, None]
+        for n, (which, pool, norm) in enumerate(((1, self.pool_k, getattr(self, "norm_k", None)),
+                                                 (2, self.pool_v, getattr(self, "norm_v", None)))):
+            with torch.cuda.stream(side[n]):
+                side[n].wait_event(fork)
+                outs[n], _ = self._pooled(qkv5, which, pool, norm, thw_shape)
+                outs[n].record_stream(cur)
         q, out_shape = self._pooled(qkv5, 0, self.pool_q, getattr(self, "norm_q", None), thw_shape)
-        k, _ = self._pooled(qkv5, 1, self.pool_k, getattr(self, "norm_k", None), thw_shape)
-        v, _ = self._pooled(qkv5, 2, self.pool_v, getattr(self, "norm_v", None), thw_shape)
+        for n in range(2):
+            cur.wait_stream(side[n])
+        qkv.record_stream(side[0])
+        qkv.record_stream(side[1])
+        k, v = outs
         y = ops.attention(q, k, v, self.scale, self.use_query_residual_pool)
         return y, out_shape
 
