@@ -129,13 +129,25 @@ def run_reference(args):
     return 0
 
 
-def summarize_events(log, peaks, steps, clips_per_step):
+def summarize_events(log, peaks, steps, base):
+    """Per kernel family: launches, device time (union of the [start, end] intervals, so launches that overlap on
+    side streams are not double counted) and achieved throughput of the algorithmic work."""
     out = {}
     for cat, evs in log.items():
-        ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+        spans = sorted((base.elapsed_time(a), base.elapsed_time(b)) for a, b, _ in evs)
+        ms, cur_a, cur_b = 0.0, None, None
+        for a, b in spans:
+            if cur_b is None or a > cur_b:
+                if cur_b is not None:
+                    ms += cur_b - cur_a
+                cur_a, cur_b = a, b
+            else:
+                cur_b = max(cur_b, b)
+        if cur_b is not None:
+            ms += cur_b - cur_a
         work = sum(w for _, _, w in evs)
         ent = {"launches_per_step": len(evs) / steps, "ms_per_step": ms / steps}
-        if cat.startswith("pool") or cat == "layernorm":
+        if cat.startswith("pool") or cat in ("layernorm", "fold_clip", "im2col"):
             ent.update(bound="hbm", achieved=work / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
         else:
             ent.update(bound="tensor", achieved=work / (ms * 1e-3) / 1e12, peak=peaks["bf16_tflops_sustained"],
@@ -254,7 +266,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    kernels = summarize_events(log, peaks, K, B)
+    kernels = summarize_events(log, peaks, K, i0)
     attn = kernels.get("attention", {})
     roofline = {"kernel": "attention_tc_kernel (fused tcgen05 pooling attention)", "bound": "tensor",
                 "achieved": attn.get("achieved"), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
