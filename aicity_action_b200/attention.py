@@ -18,9 +18,9 @@ import numpy
 import torch
 import torch.nn as nn
 
+from . import autograd as AG
 from . import ops
 from .common import DropPath, Mlp, drop_path_scale
-from .weights import cached_weight
 
 
 def _compute_dtype(x: torch.Tensor) -> torch.dtype:
@@ -44,12 +44,6 @@ def _side_streams(device):
     if key not in _SIDE:
         _SIDE[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
     return _SIDE[key]
-
-
-def _no_grad_only(*tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            "aicity_action_b200: backward kernels are not part of this build; run under torch.no_grad()")
 
 
 def _pool_desc(pool):
@@ -86,9 +80,15 @@ def attention_pool(tensor, pool, thw_shape, has_cls_embed=True, norm=None, pool2
         return tensor, thw_shape
     if pool2d is not None:
         raise NotImplementedError("pool2d (the reference's ONNX/TNN export aid) is not supported")
-    _no_grad_only(tensor)
     desc = _pool_desc(pool)
     mode, k, s, w = desc
+    if AG.recording(tensor, w, getattr(norm, "weight", None)):
+        # differentiable form: the block's skip-path max pool; q/k/v pooling trains through MultiScaleAttention
+        if tensor.ndim == 3 and mode == "max" and norm is None and not has_cls_embed:
+            return AG.maxpool_tokens(tensor, list(thw_shape), k, s)
+        raise NotImplementedError(
+            "attention_pool: this variant has no backward kernel yet (trainable: MultiScaleAttention's conv pooling "
+            "without cls token, and the [B, L, C] max-pool skip path)")
     ln = None
     if norm is not None:
         ln = (norm.weight, norm.bias, norm.eps)
@@ -171,11 +171,34 @@ class MultiScaleAttention(nn.Module):
             return out, list(thw_shape)
         return attention_pool(t, pool, thw_shape, has_cls_embed=self.has_cls_embed, norm=norm)
 
+    def _train_descs(self):
+        """Pooling description of q / k / v for the differentiable path (AG.pool_qkv)."""
+        descs, params = [], []
+        for pool, norm in ((self.pool_q, getattr(self, "norm_q", None)), (self.pool_k, getattr(self, "norm_k", None)),
+                           (self.pool_v, getattr(self, "norm_v", None))):
+            if pool is None:
+                descs.append(None)
+                params += [None, None, None]
+                continue
+            mode, k, s, w = _pool_desc(pool)
+            if mode != "conv" or self.has_cls_embed:
+                raise NotImplementedError("training is implemented for MVIT.MODE == 'conv' without a cls token")
+            descs.append((tuple(k), tuple(s), norm.eps if norm is not None else None))
+            params += [w, getattr(norm, "weight", None), getattr(norm, "bias", None)]
+        return tuple(descs), params
+
     def attend(self, x, thw_shape):
         """Everything before `proj`: returns (y [B, Lq, C], out_thw) with y = softmax(qkᵀ·scale)v (+q)."""
         B, N, _ = x.shape
         C, h = self.dim_out, self.num_heads
-        qkv = ops.linear(x, cached_weight(self.qkv.weight, x.dtype), self.qkv.bias)
+        qkv = AG.linear(x, self.qkv.weight, self.qkv.bias)
+        pool_params = [p for m in (self.pool_q, self.pool_k, self.pool_v, getattr(self, "norm_q", None),
+                                   getattr(self, "norm_k", None), getattr(self, "norm_v", None)) if m is not None
+                       for p in m.parameters()]
+        if AG.recording(qkv, *pool_params):
+            descs, params = self._train_descs()
+            (q, k, v), shapes = AG.pool_qkv(qkv, h, thw_shape, descs, params)
+            return AG.attention(q, k, v, self.scale, self.use_query_residual_pool), shapes[0]
         qkv5 = qkv.view(B, N, 3, h, C // h)
         # the three pooling launches are independent: K and V run on side streams next to Q so the small
         # deep-stage launches overlap instead of queueing (fork / join with events, graph-capturable)
@@ -202,13 +225,11 @@ class MultiScaleAttention(nn.Module):
     def forward(self, x, thw_shape, residual=None, row_scale=None):
         """Reference contract: (x [B,N,dim], thw) -> (proj(attn) [B,Lq,dim_out], thw').
         `residual` / `row_scale` (used by MultiScaleBlock) fold `x_res + drop_path(.)` into the proj GEMM."""
-        _no_grad_only(x)
         if self.drop_rate > 0.0 and self.training:
             raise NotImplementedError("proj dropout in training is not supported by the B200 path yet")
         dt = _compute_dtype(x)
         y, out_shape = self.attend(x.to(dt), thw_shape)
-        out = ops.linear(y, cached_weight(self.proj.weight, dt), self.proj.bias, residual=residual,
-                         row_scale=row_scale)
+        out = AG.linear(y, self.proj.weight, self.proj.bias, residual=residual, row_scale=row_scale)
         return out, out_shape
 
 
@@ -265,8 +286,12 @@ class MultiScaleBlock(nn.Module):
         s = [p.stride] * 3 if isinstance(p.stride, int) else list(p.stride)
         return all(v == 1 for v in k) and all(v == 1 for v in s)   # MaxPool3d([1,1,1]) == identity (D6)
 
+    def out_thw(self, thw_shape):
+        """Token grid after this block (the q pooling decides it), without running it."""
+        desc = _pool_desc(self.attn.pool_q)
+        return list(thw_shape) if desc is None else ops.pooled_thw(list(thw_shape), desc[1], desc[2])
+
     def forward(self, x, thw_shape):
-        _no_grad_only(x)
         dt = _compute_dtype(x)
         x = x.to(dt).contiguous()
         B = x.shape[0]
@@ -275,18 +300,18 @@ class MultiScaleBlock(nn.Module):
         s_attn = drop_path_scale(B, p_drop, self.training, x.device)
         s_mlp = drop_path_scale(B, p_drop, self.training, x.device)
 
-        xn = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        xn = AG.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         if self.expand_channel and not self.pool_skip_use_conv:
-            x = ops.linear(x, cached_weight(self.proj_max_pool.weight, dt), self.proj_max_pool.bias)
+            x = AG.linear(x, self.proj_max_pool.weight, self.proj_max_pool.bias)
         if self._skip_is_identity():
             x_res = x
         else:
             x_res, _ = attention_pool(x, self.pool_skip, thw_shape, has_cls_embed=self.has_cls_embed)
         # x = x_res + drop_path(proj(attn))  — residual and DropPath scale live in the proj GEMM epilogue
         x, thw_new = self.attn(xn, thw_shape, residual=x_res, row_scale=s_attn)
-        x_norm = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        x_norm = AG.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         if self.dim != self.dim_out:
-            x = ops.linear(x_norm, cached_weight(self.proj.weight, dt), self.proj.bias)
+            x = AG.linear(x_norm, self.proj.weight, self.proj.bias)
         # out = x + drop_path(mlp(x_norm)) — residual and scale in the fc2 GEMM epilogue
         out = self.mlp(x_norm, residual=x, row_scale=s_mlp)
         return out, thw_new

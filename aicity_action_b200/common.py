@@ -4,8 +4,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops
-from .weights import cached_weight
+from . import autograd as AG
 
 
 def drop_path_scale(batch: int, drop_prob: float, training: bool, device, dtype=torch.float32):
@@ -57,6 +56,5 @@ class Mlp(nn.Module):
         """Returns fc2(gelu(fc1(x))) * row_scale + residual."""
         if self.drop_rate > 0.0 and self.training:
             raise NotImplementedError("MVIT.DROPOUT_RATE > 0 in training is not supported by the B200 path yet")
-        h = ops.linear(x, cached_weight(self.fc1.weight, x.dtype), self.fc1.bias, gelu=True)
-        return ops.linear(h, cached_weight(self.fc2.weight, x.dtype), self.fc2.bias,
-                          residual=residual, row_scale=row_scale)
+        h = AG.linear(x, self.fc1.weight, self.fc1.bias, gelu=True)
+        return AG.linear(h, self.fc2.weight, self.fc2.bias, residual=residual, row_scale=row_scale)

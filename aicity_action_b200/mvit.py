@@ -13,11 +13,12 @@ from functools import partial
 
 import torch
 import torch.nn as nn
+import torch.utils.checkpoint
 from torch.nn.init import trunc_normal_
 
+from . import autograd as AG
 from . import ops
-from .attention import MultiScaleBlock, _compute_dtype, _no_grad_only
-from .weights import cached_weight
+from .attention import MultiScaleBlock, _compute_dtype
 
 
 def round_width(width, multiplier, min_width=1, divisor=1, verbose=False):
@@ -153,6 +154,13 @@ class TransformerBasicHead(nn.Module):
         act = self.use_act_in_train or not self.training
         drop = hasattr(self, "dropout") and self.training and self.dropout.p > 0
         softmax = act and isinstance(self.act, nn.Softmax)
+        if AG.recording(x, self.projection.weight, self.projection.bias):
+            # differentiable path: a [B, C] mean and an 18-way projection — microseconds, left to autograd in fp32
+            feat = x.float().mean(1)
+            if drop:
+                feat = self.dropout(feat)
+            out = torch.nn.functional.linear(feat, self.projection.weight, self.projection.bias)
+            return self.act(out) if act else out
         if not drop:
             out = ops.mean_head(x, self.projection.weight, self.projection.bias, softmax=softmax)
         else:
@@ -345,7 +353,15 @@ class MViT(nn.Module):
 
     def forward_features(self, x, dtype):
         T, H, W = self.patch_dims
-        if self.sep_pos_embed and not self.cls_embed_on:
+        stem_params = [self.patch_embed.proj.weight, self.patch_embed.proj.bias]
+        stem_params += [self.pos_embed_spatial, self.pos_embed_temporal] if self.sep_pos_embed else [self.pos_embed]
+        if AG.recording(*stem_params):
+            if not self.sep_pos_embed or self.cls_embed_on:
+                raise NotImplementedError("training is implemented for SEP_POS_EMBED without a cls token "
+                                          "(the Aicity configs)")
+            x = AG.patch_embed(self.patch_embed, x, dtype, self.pos_embed_spatial, self.pos_embed_temporal,
+                               self._pos_tokens(dtype))
+        elif self.sep_pos_embed and not self.cls_embed_on:
             # bias + positional embedding ride in the patch-embed GEMM epilogue
             pos = self._pos_tokens(dtype)
             x = self.patch_embed(x, dtype, pos=pos, pos_period=pos.shape[0])
@@ -360,19 +376,24 @@ class MViT(nn.Module):
         if self.drop_rate and self.training:
             x = self.pos_drop(x)
         if self.norm_stem is not None:
-            x = ops.layernorm(x, self.norm_stem.weight, self.norm_stem.bias, self.norm_stem.eps)
+            x = AG.layernorm(x, self.norm_stem.weight, self.norm_stem.bias, self.norm_stem.eps)
         thw = [T, H, W]
         for blk in self.blocks:
-            x, thw = blk(x, thw)
+            if self.act_checkpoint and x.requires_grad and torch.is_grad_enabled():
+                # MODEL.ACT_CHECKPOINT (video_model_builder.py:988-1036 wraps every block in fairscale's checkpoint_wrapper)
+                thw_in = list(thw)
+                x = torch.utils.checkpoint.checkpoint(lambda t, b=blk, s=thw_in: b(t, s)[0], x, use_reentrant=False)
+                thw = blk.out_thw(thw_in)
+            else:
+                x, thw = blk(x, thw)
         if self.norm is not None:
-            x = ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps)
+            x = AG.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         return x, thw
 
     def forward(self, x, bboxes=None, dataset_name=None, run_cross_proj=False, use_moco=False,
                 moco_momentum=0.9):
         if not self.direct_input:
             x = x[0]
-        _no_grad_only(x)
         dtype = _compute_dtype(x)
         x, _ = self.forward_features(x, dtype)
         if self.cls_embed_on:

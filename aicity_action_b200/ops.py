@@ -310,3 +310,82 @@ def patch_conv(folded: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tens
               "mvit_patch_conv_fwd")
     launch_count += 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------ backward
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float):
+    """-> (dx like x, dgamma fp32 [C], dbeta fp32 [C])."""
+    global launch_count
+    _need_cuda(x, gamma, dy)
+    x, dy = x.contiguous(), dy.contiguous()
+    assert x.shape == dy.shape and x.dtype == dy.dtype
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    dgb = torch.zeros((2, C), dtype=torch.float32, device=x.device)
+    with _Timed("layernorm_bwd", 3.0 * x.numel() * x.element_size()):
+        check(_lib.load().mvit_layernorm_bwd(_ptr(x), _ptr(_f32c(gamma)), _ptr(dy), _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]),
+                                             rows, C, float(eps), _dt(x), _stream()), "mvit_layernorm_bwd")
+    launch_count += 1
+    return dx, dgb[0], dgb[1]
+
+
+def gelu_bwd(pre: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    global launch_count
+    _need_cuda(pre, dy)
+    pre, dy = pre.contiguous(), dy.contiguous()
+    assert pre.shape == dy.shape and pre.dtype == dy.dtype
+    out = torch.empty_like(pre)
+    with _Timed("gelu_bwd", 3.0 * pre.numel() * pre.element_size()):
+        check(_lib.load().mvit_gelu_bwd(_ptr(pre), _ptr(dy), _ptr(out), pre.numel(), _dt(pre), _stream()), "mvit_gelu_bwd")
+    launch_count += 1
+    return out
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool):
+    """dy [..., N], x [..., K] -> (dw fp32 [N, K], db fp32 [N] | None)."""
+    global launch_count
+    _need_cuda(dy, x)
+    dy, x = dy.contiguous(), x.contiguous()
+    N, K = dy.shape[-1], x.shape[-1]
+    M = x.numel() // K
+    assert dy.numel() == M * N and dy.dtype == x.dtype
+    dw = torch.zeros((N, K), dtype=torch.float32, device=x.device)
+    db = torch.zeros((N,), dtype=torch.float32, device=x.device) if want_bias else None
+    with _Timed("linear_wgrad", 2.0 * M * N * K):
+        check(_lib.load().mvit_linear_wgrad(_ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, _dt(x), _stream()),
+              "mvit_linear_wgrad")
+    launch_count += 1
+    return dw, db
+
+
+def attention_bwd(q, k, v, out, dout, lse, scale: float, add_q: bool):
+    """-> (dq, dk, dv) in q.dtype, shapes of q / k / v."""
+    global launch_count
+    _need_cuda(q, k, v, out, dout, lse)
+    dout = dout.contiguous()
+    B, h, Lq, d = q.shape
+    Lk = k.shape[2]
+    dq = torch.empty_like(q)
+    dkv = torch.zeros((2, B, h, Lk, d), dtype=torch.float32, device=q.device)
+    with _Timed("attention_bwd", 10.0 * B * h * Lq * Lk * d):
+        check(_lib.load().mvit_attention_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dq),
+                                             _ptr(dkv[0]), _ptr(dkv[1]), B, h, Lq, Lk, d, float(scale), 1 if add_q else 0,
+                                             _dt(q), _stream()), "mvit_attention_bwd")
+    launch_count += 1
+    return dq, dkv[0].to(q.dtype), dkv[1].to(q.dtype)
+
+
+def attention_pool_bwd(what: int, x: Optional[torch.Tensor], strides: Tuple[int, int, int], dy: torch.Tensor,
+                       weight: Optional[torch.Tensor], dx: Optional[torch.Tensor], dw: Optional[torch.Tensor], B: int,
+                       heads: int, d: int, thw: Sequence[int], kernel: Sequence[int], stride: Sequence[int]):
+    """Raw form of mvit_attention_pool_bwd; x / dx are addressed through `strides` = (batch, token, head)."""
+    global launch_count
+    _need_cuda(x, dy, weight, dx, dw)
+    assert dy.is_contiguous()
+    weight = _f32c(weight)
+    with _Timed("pool_bwd", 0.0):
+        check(_lib.load().mvit_attention_pool_bwd(what, _ptr(x), strides[0], strides[1], strides[2], _ptr(dy), _ptr(weight),
+                                                  _ptr(dx), _ptr(dw), B, heads, d, thw[0], thw[1], thw[2], *kernel, *stride,
+                                                  _dt(dy), _stream()), "mvit_attention_pool_bwd")
+    launch_count += 1

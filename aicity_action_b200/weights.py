@@ -21,3 +21,17 @@ def cached_weight(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         except AttributeError:      # plain tensors without __dict__ are converted every call
             pass
     return slot[1]
+
+
+def cached_weight_t(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """`param` [N, K] as a contiguous [K, N] `dtype` tensor — the operand of the input-gradient GEMM
+    dx = dy · W (a Linear whose weight is Wᵀ).  Cached like `cached_weight`."""
+    key = (dtype, param._version, param.device, param.data_ptr())
+    slot = getattr(param, _ATTR + "_t", None)
+    if slot is None or slot[0] != key:
+        slot = (key, param.detach().to(dtype).t().contiguous())
+        try:
+            setattr(param, _ATTR + "_t", slot)
+        except AttributeError:
+            pass
+    return slot[1]

@@ -166,6 +166,43 @@ int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, c
                         int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N,
                         void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward entry points (the reference has no explicit backward code: tools/train_net.py:229-246 calls
+ * loss.backward() and autograd differentiates attention.py / common.py op by op; these are those
+ * derivatives, one launch per fused forward op).  Activations / activation gradients are `dtype`;
+ * parameter gradients are fp32 and ACCUMULATED (+=) into caller-zeroed buffers.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* LayerNorm backward (nn.LayerNorm at attention.py:421,436,66-67): x, dy, dx [rows, channels]; dgamma/dbeta += */
+int mvit_layernorm_bwd(const void *x, const float *gamma, const void *dy, void *dx, float *dgamma,
+                       float *dbeta, int64_t rows, int channels, float eps, int dtype, void *stream);
+
+/* exact-erf GELU backward (common.py:20): dpre = dy * gelu'(pre), n elements */
+int mvit_gelu_bwd(const void *pre, const void *dy, void *dpre, int64_t n, int dtype, void *stream);
+
+/* nn.Linear parameter gradients: dw[N,K] += dy[M,N]^T x[M,K];  db[N] += column sums of dy (db may be NULL).
+ * (the input gradient dx = dy . W is mvit_linear_fwd with the transposed weight) */
+int mvit_linear_wgrad(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int dtype,
+                      void *stream);
+
+/* Backward of mvit_attention_fwd (attention.py:267-279).  q/k/v/out as in the forward, dout [B, Lq, heads*d],
+ * lse from the forward; dq [B, heads, Lq, d] (dtype, overwritten; includes the +q residual path),
+ * dk/dv [B, heads, Lk, d] fp32, caller-zeroed, accumulated. */
+int mvit_attention_bwd(const void *q, const void *k, const void *v, const void *out, const void *dout,
+                       const float *lse, void *dq, float *dk, float *dv, int B, int heads, int Lq, int Lk,
+                       int d, float scale, int add_q_residual, int dtype, void *stream);
+
+/* Backward pieces of mvit_attention_pool_fwd (attention.py:12-83), geometry arguments as in the forward
+ * (padding = kernel/2, no cls token):
+ *   what 0: depthwise-conv input gradient, dx written through the forward's input strides (x_bs, x_ls, x_hs);
+ *   what 1: depthwise-conv weight gradient dw[d, taps] += (x read through the strides);
+ *   what 2: max-pool input gradient into a caller-zeroed dense fp32 dx [B, L, heads, d] (arg-max recomputed from x).
+ * dy is the gradient w.r.t. the pooled (pre-LayerNorm) output: [B, heads, L', d] for what 0/1, token layout
+ * [B, L', heads*d] for what 2 (the block's skip path pools [B, L, C] tokens). */
+int mvit_attention_pool_bwd(int what, const void *x, int64_t x_bs, int64_t x_ls, int64_t x_hs, const void *dy,
+                            const float *weight, void *dx, float *dw, int B, int heads, int d, int T, int H,
+                            int W, int kt, int kh, int kw, int st, int sh, int sw, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

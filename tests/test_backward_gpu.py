@@ -1,0 +1,314 @@
+"""GPU parity of the backward kernels: gradients from libmvit_b200.so vs autograd through the CPU oracle
+(the reference differentiates this path with plain autograd: tools/train_net.py:229-246)."""
+from functools import partial
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mvit_oracle as O
+from aicity_action_b200 import autograd as AG
+from aicity_action_b200 import ops
+from aicity_action_b200.attention import MultiScaleBlock
+from aicity_action_b200.config import aicity_cfg
+from aicity_action_b200.mvit import MViT
+from tests.conftest import rel_inf
+from tests.golden.cases import BLOCK_CASES, MODEL_CASES, tiny_cfg_overrides
+from tests.golden.synth import synth_clip, synth_input, synth_state_dict, synth_tensor
+
+pytestmark = pytest.mark.gpu
+# tolerance on ‖Δ‖∞/‖ref‖∞ of every gradient tensor: fp32 1e-4, bf16 2e-2 (north_star)
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+IDS = ["f32", "bf16"]
+
+
+def leaf(t, dtype=None, cuda=False):
+    t = t.detach().clone()
+    if dtype is not None:
+        t = t.to(dtype)
+    if cuda:
+        t = t.cuda()
+    return t.requires_grad_(True)
+
+
+def check(name, got, ref, tol, floor=0.0, l2=False):
+    """‖got − ref‖∞ / max(‖ref‖∞, floor) < tol (or the same ratio of 2-norms when `l2`).  `floor` guards gradients that are analytically zero (e.g. norm_k.bias:
+    a constant added to every key cancels in the softmax), whose reference value is pure rounding noise."""
+    assert got is not None, f"{name}: no gradient"
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    if l2:
+        err = (got - ref).norm().item() / max(ref.norm().item(), floor * ref.numel() ** 0.5, 1e-30)
+    else:
+        err = (got - ref).abs().max().item() / max(ref.abs().max().item(), floor, 1e-30)
+    assert err < tol, f"{name}: rel-{'l2' if l2 else 'inf'} error {err:.3e} >= {tol}"
+
+
+def grad_floor(ref_grads):
+    """1e-3 of the largest gradient magnitude in the module."""
+    return 1e-3 * max(g.abs().max().item() for g in ref_grads)
+
+
+def param_floor(name, floor):
+    """norm_k.bias has an analytically zero gradient (the reference's own value is ~1e-8 rounding noise): require it to be
+    small against the module's gradient scale instead of against that noise."""
+    return floor * 1e3 if name.endswith("norm_k.bias") else floor
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("rows,C", [(300, 96), (77, 768), (64, 100)])
+def test_layernorm_bwd(rows, C, dtype):
+    x, g, b, dy = (synth_tensor(1, n, s) for n, s in (("x", (rows, C)), ("g", (C,)), ("b", (C,)), ("dy", (rows, C))))
+    g = g + 1.0
+    xr, gr, br = leaf(x.to(dtype).float()), leaf(g), leaf(b)
+    F.layer_norm(xr, (C,), gr, br, 1e-6).backward(dy.to(dtype).float())
+    xc, gc, bc = leaf(x, dtype, True), leaf(g, None, True), leaf(b, None, True)
+    AG.layernorm(xc, gc, bc, 1e-6).backward(dy.cuda().to(dtype))
+    for n, a, r in (("dx", xc.grad, xr.grad), ("dgamma", gc.grad, gr.grad), ("dbeta", bc.grad, br.grad)):
+        check(n, a, r, TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("shape", [(2, 150, 96, 288), (3, 64, 192, 768), (1, 33, 768, 18)], ids=str)
+@pytest.mark.parametrize("epi", ["plain", "gelu", "residual_droppath"])
+def test_linear_bwd(shape, epi, dtype):
+    B, L, K, N = shape
+    x, w, b, dy, res = (synth_tensor(2, n, s) for n, s in (("x", (B, L, K)), ("w", (N, K)), ("b", (N,)),
+                                                           ("dy", (B, L, N)), ("res", (B, L, N))))
+    w = w * K ** -0.5
+    scale = torch.tensor([0.0, 1.25, 1.25][:B] if B > 1 else [1.25])
+    xr, wr, br, rr = leaf(x.to(dtype).float()), leaf(w), leaf(b), leaf(res.to(dtype).float())
+    y = F.linear(xr, wr.to(dtype).float(), br)
+    if epi == "gelu":
+        y = F.gelu(y)
+    if epi == "residual_droppath":
+        y = y * scale.view(B, 1, 1) + rr
+    y.backward(dy.to(dtype).float())
+    xc, wc, bc, rc = leaf(x, dtype, True), leaf(w, None, True), leaf(b, None, True), leaf(res, dtype, True)
+    if epi == "residual_droppath":
+        yc = AG.linear(xc, wc, bc, residual=rc, row_scale=scale.cuda())
+    else:
+        yc = AG.linear(xc, wc, bc, gelu=epi == "gelu")
+    yc.backward(dy.cuda().to(dtype))
+    tol = TOL[dtype]
+    check("dx", xc.grad, xr.grad, tol)
+    check("dw", wc.grad, wr.grad, tol)
+    check("db", bc.grad, br.grad, tol)
+    if epi == "residual_droppath":
+        check("dres", rc.grad, rr.grad, tol)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("B,h,Lq,Lk,add_q", [(2, 2, 200, 72, True), (1, 3, 65, 130, False), (1, 1, 1024, 64, True)])
+def test_attention_bwd(B, h, Lq, Lk, add_q, dtype):
+    d = 96
+    q, k, v, do = (synth_tensor(3, n, s) for n, s in (("q", (B, h, Lq, d)), ("k", (B, h, Lk, d)), ("v", (B, h, Lk, d)),
+                                                      ("do", (B, Lq, h * d))))
+    qr, kr, vr = (leaf(t.to(dtype).float()) for t in (q, k, v))
+    a = ((qr @ kr.transpose(-2, -1)) * d ** -0.5).softmax(-1)
+    y = (a @ vr).transpose(1, 2).reshape(B, Lq, h * d)
+    if add_q:
+        y = y + qr.transpose(1, 2).reshape(B, Lq, h * d)
+    y.backward(do.to(dtype).float())
+    qc, kc, vc = (leaf(t, dtype, True) for t in (q, k, v))
+    AG.attention(qc, kc, vc, d ** -0.5, add_q).backward(do.cuda().to(dtype))
+    for n, a_, r in (("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)):
+        check(n, a_, r, TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("thw,sq,skv,heads,pool_q", [((4, 8, 8), (1, 1, 1), (1, 2, 2), 2, True),
+                                                      ((4, 8, 8), (1, 2, 2), (1, 4, 4), 1, True),
+                                                      ((3, 7, 5), (2, 2, 2), (1, 2, 2), 2, True),
+                                                      ((4, 8, 8), None, (1, 2, 2), 2, False)], ids=str)
+def test_pool_qkv_bwd(thw, sq, skv, heads, pool_q, dtype):
+    d, B = 96, 2
+    N = thw[0] * thw[1] * thw[2]
+    qkv = synth_tensor(4, "qkv", (B, N, 3 * heads * d))
+    names = ("q", "k", "v")
+    strides = (sq, skv, skv)
+    w = {n: synth_tensor(4, "w" + n, (d, 1, 3, 3, 3)) * 0.3 for n in names}
+    g = {n: synth_tensor(4, "g" + n, (d,)) + 1.0 for n in names}
+    b = {n: synth_tensor(4, "b" + n, (d,)) for n in names}
+    up = {}
+    # oracle
+    qr = leaf(qkv.to(dtype).float())
+    wr, gr, br = ({n: leaf(t[n]) for n in names} for t in (w, g, b))
+    parts = qr.reshape(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
+    loss = 0
+    for i, n in enumerate(names):
+        if strides[i] is None:
+            o = parts[i]
+        else:
+            o, _ = O.attention_pool(parts[i], thw, mode="conv", kernel=[3, 3, 3], stride=list(strides[i]), weight=wr[n],
+                                    ln=(gr[n], br[n], 1e-5))
+        up[n] = synth_tensor(4, "up" + n, tuple(o.shape))
+        loss = loss + (o * up[n].to(dtype).float()).sum()
+    loss.backward()
+    # CUDA
+    qc = leaf(qkv, dtype, True)
+    wc, gc, bc = ({n: leaf(t[n], None, True) for n in names} for t in (w, g, b))
+    descs, params = [], []
+    for i, n in enumerate(names):
+        if strides[i] is None:
+            descs.append(None)
+            params += [None, None, None]
+        else:
+            descs.append(((3, 3, 3), tuple(strides[i]), 1e-5))
+            params += [wc[n], gc[n], bc[n]]
+    outs, shapes = AG.pool_qkv(qc, heads, list(thw), tuple(descs), params)
+    torch.autograd.backward(outs, [up[n].cuda().to(dtype) for n in names])
+    tol = TOL[dtype]
+    check("dqkv", qc.grad, qr.grad, tol)
+    for i, n in enumerate(names):
+        if strides[i] is not None:
+            check("dw_" + n, wc[n].grad, wr[n].grad, tol)
+            check("dgamma_" + n, gc[n].grad, gr[n].grad, tol)
+            check("dbeta_" + n, bc[n].grad, br[n].grad, tol)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("thw,kernel,stride,C", [((4, 8, 8), (1, 3, 3), (1, 2, 2), 192), ((3, 7, 5), (1, 3, 3), (1, 2, 2), 96),
+                                                 ((4, 8, 8), (3, 3, 3), (2, 2, 2), 96)], ids=str)
+def test_maxpool_tokens_bwd(thw, kernel, stride, C, dtype):
+    B, N = 2, thw[0] * thw[1] * thw[2]
+    x = synth_tensor(5, "x", (B, N, C))
+    xr = leaf(x.to(dtype).float())
+    o, _ = O.attention_pool(xr, thw, mode="max", kernel=list(kernel), stride=list(stride))
+    up = synth_tensor(5, "up", tuple(o.shape))
+    o.backward(up.to(dtype).float())
+    xc = leaf(x, dtype, True)
+    oc, _ = AG.maxpool_tokens(xc, list(thw), list(kernel), list(stride))
+    oc.backward(up.cuda().to(dtype))
+    check("dx", xc.grad, xr.grad, TOL[dtype])
+
+
+def load_synth(m, seed):
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed)
+    m.load_state_dict(sd, strict=True)
+    return sd
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("c", [c for c in BLOCK_CASES if not c["cls"]], ids=lambda c: c["name"])
+def test_block_bwd(c, dtype):
+    m = MultiScaleBlock(dim=c["dim"], dim_out=c["dim_out"], num_heads=c["heads"], qkv_bias=True,
+                        norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), kernel_q=c["kernel_q"],
+                        kernel_kv=c["kernel_kv"], stride_q=c["stride_q"], stride_kv=c["stride_kv"], mode="conv",
+                        has_cls_embed=False, use_query_residual_pool=c["residual"],
+                        channel_expand_front=c["expand_front"]).train()
+    sd = load_synth(m, c["seed"])
+    m = m.cuda()
+    N = c["thw"][0] * c["thw"][1] * c["thw"][2]
+    x = synth_input(c["seed"], c["name"], (c["B"], N, c["dim"]))
+    # oracle autograd (fp32 CPU)
+    spec = O.BlockSpec(c["dim"], c["dim_out"], c["heads"], c["kernel_q"], c["kernel_kv"], c["stride_q"], c["stride_kv"], 0.0,
+                       expand=bool(c["expand_front"] and c["dim"] != c["dim_out"]))
+    mv = O.MViTSpec(blocks=[spec], patch_dims=c["thw"], embed_dim=c["dim"], patch_kernel=[3, 7, 7], patch_stride=[2, 4, 4],
+                    patch_padding=[1, 3, 3], cls_embed_on=False, sep_pos_embed=True, mode="conv",
+                    q_pool_residual=c["residual"], num_classes=18, final_norm=True)
+    sdr = {k: leaf(v) for k, v in sd.items()}
+    xr = leaf(x.to(dtype).float())
+    out_r, _ = O.multiscale_block(xr, c["thw"], sdr, "", spec, mv)
+    up = synth_tensor(c["seed"], "up", tuple(out_r.shape))
+    out_r.backward(up)
+    xc = leaf(x, dtype, True)
+    out, _ = m(xc, list(c["thw"]))
+    assert rel_inf(out.detach(), out_r.detach()) < TOL[dtype]
+    out.backward(up.cuda().to(dtype))
+    # fp32: rel-inf 1e-4 on every gradient.  bf16: the skip-path max pool picks its arg-max among bf16-rounded values, so a
+    # near-tie routes one element's gradient to a neighbour (true of any bf16 implementation); whole-block bf16 gradients
+    # are therefore judged in the 2-norm, single ops (above) in the inf-norm.
+    l2 = dtype == torch.bfloat16
+    tol = 8e-2 if l2 else TOL[dtype]       # measured <= 5.3e-2 (the block with the max-pool skip), others <= 2e-2
+    check("dx", xc.grad, xr.grad, tol, l2=l2)
+    floor = grad_floor([sdr[k].grad for k, _ in m.named_parameters()])
+    for k, p in m.named_parameters():
+        check(k, p.grad, sdr[k].grad, tol, param_floor(k, floor), l2=l2)
+
+
+TRAIN_OVR = ["MVIT.DROPPATH_RATE", 0.0, "MODEL.DROPOUT_RATE", 0.0]
+
+
+def _train_model(c, extra=()):
+    cfg = aicity_cfg(c["yaml"], tiny_cfg_overrides(c) + TRAIN_OVR + list(extra))
+    m = MViT(cfg).train()
+    sd = load_synth(m, c["seed"])
+    return cfg, m.cuda(), sd
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("c", MODEL_CASES[:2], ids=lambda c: c["name"])
+def test_mvit_loss_and_gradients(c, dtype):
+    """One training forward/backward of the (tiny) model: cross-entropy loss and every parameter gradient."""
+    cfg, m, sd = _train_model(c)
+    x = synth_clip(c["seed"], c["B"], cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE)
+    labels = torch.arange(c["B"]) % cfg.MODEL.NUM_CLASSES
+    sdr = {k: leaf(v) for k, v in sd.items()}
+    logits_r = O.mvit_forward(x, sdr, O.derive_spec(cfg), training=True)
+    loss_r = F.cross_entropy(logits_r, labels)
+    loss_r.backward()
+    logits = m([x.cuda().to(dtype)])
+    assert logits.dtype == torch.float32 and logits.requires_grad
+    loss = F.cross_entropy(logits, labels.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_r.item()) < (1e-4 if dtype == torch.float32 else 2e-2) * max(1.0, abs(loss_r.item()))
+    # fp32 is the exactness proof (rel-inf 1e-4 on every parameter gradient).  bf16 is judged in the 2-norm (see
+    # test_block_bwd): roundings compound through four blocks forward and backward (tools/grad_report.py prints the table).
+    l2 = dtype == torch.bfloat16
+    # yardstick: PyTorch's own bf16 evaluation of the reference graph (CPU) deviates from its fp32 gradients by 1e-2 (head)
+    # to 1.1e-1 (block 0 / patch embed) rel-l2 on this model; the CUDA path measures 2e-3 .. 9e-2.
+    tol = 1.5e-1 if l2 else 1e-4
+    floor = grad_floor([sdr[k].grad for k, _ in m.named_parameters()])
+    for k, p in m.named_parameters():
+        check(k, p.grad, sdr[k].grad, tol, param_floor(k, floor), l2=l2)
+
+
+def test_activation_checkpoint_matches_plain():
+    c = MODEL_CASES[0]
+    cfg, m, _ = _train_model(c)
+    _, mc, _ = _train_model(c, ["MODEL.ACT_CHECKPOINT", True])
+    x = synth_clip(c["seed"], c["B"], cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda().bfloat16()
+    labels = (torch.arange(c["B"]) % cfg.MODEL.NUM_CLASSES).cuda()
+    la = F.cross_entropy(m([x]), labels)
+    la.backward()
+    lb = F.cross_entropy(mc([x]), labels)
+    lb.backward()
+    assert torch.equal(la, lb)
+    floor = grad_floor([p.grad for p in m.parameters()])
+    for (k, p), (_, q) in zip(m.named_parameters(), mc.named_parameters()):
+        check(k, q.grad, p.grad, 1e-2, param_floor(k, floor))           # atomics: summation order differs run to run
+
+
+def test_training_steps_reduce_loss():
+    """AdamW on the B200 path (the reference's optimiser, tools/train_net.py + models/optimizer.py) overfits one batch."""
+    c = MODEL_CASES[0]
+    cfg, m, _ = _train_model(c)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.05)
+    x = synth_clip(c["seed"], 4, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda()
+    labels = torch.tensor([0, 5, 9, 17]).cuda()
+    losses = []
+    for _ in range(12):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = m([x])
+        loss = F.cross_entropy(logits.float(), labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < 0.5 * losses[0], losses
+
+
+def test_inference_path_unchanged_by_autograd_routing():
+    """Under no_grad nothing is recorded and the fast forward path is used even with trainable parameters."""
+    c = MODEL_CASES[0]
+    cfg, m, _ = _train_model(c)
+    m.eval()
+    x = synth_clip(c["seed"], 2, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda().bfloat16()
+    with torch.no_grad():
+        p = m([x])
+    assert not p.requires_grad
+    q = m([x])                       # grad mode on: same numbers, now differentiable
+    assert q.requires_grad and rel_inf(q.detach(), p) < 2e-2
