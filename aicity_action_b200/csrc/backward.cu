@@ -3,6 +3,7 @@
 // (tools/train_net.py:229-246 calls loss.backward() on this path; the reference relies on autograd for every op of
 // attention.py / common.py).  Tensor-core versions of the two heavy ones (wgrad, attention backward) are the next step;
 // dgrad GEMMs already run on the forward tcgen05 kernel (dx = dy · W is a Linear with the transposed weight).
+#include "attention.cuh"
 #include "common.cuh"
 
 namespace mvit {
@@ -429,17 +430,28 @@ extern "C" int mvit_linear_wgrad(const void *dy, const void *x, float *dw, float
   return 0;
 }
 
+extern "C" size_t mvit_attention_bwd_workspace_floats(int B, int heads, int Lq) {
+  return attention_bwd_workspace_floats(B, heads, Lq);
+}
+
 extern "C" int mvit_attention_bwd(const void *q, const void *k, const void *v, const void *out, const void *dout,
-                                  const float *lse, void *dq, float *dk, float *dv, int B, int heads, int Lq, int Lk,
-                                  int d, float scale, int add_q_residual, int dtype, void *stream) {
+                                  const float *lse, void *dq, float *dk, float *dv, float *workspace, int B, int heads,
+                                  int Lq, int Lk, int d, float scale, int add_q_residual, int dtype, int impl,
+                                  void *stream) {
   MVIT_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv, "attention_bwd: null pointer");
   MVIT_REQUIRE(B >= 0 && heads > 0 && Lq > 0 && Lk > 0, "attention_bwd: bad shape");
   MVIT_REQUIRE(d == 96, "attention_bwd: head_dim %d unsupported", d);
   MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "attention_bwd: unknown dtype");
   MVIT_REQUIRE((int64_t)B * heads < 65536, "attention_bwd: B*heads too large");
   if (B == 0) return 0;
-  dim3 grid((Lq + ABQ - 1) / ABQ, B * heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl != MVIT_IMPL_SIMT) {
+    AttnBwdArgs a{q, k, v, out, dout, lse, dq, dk, dv, workspace, B, heads, Lq, Lk, scale, add_q_residual ? 1 : 0};
+    const char *why = "fp32 runs on CUDA cores";
+    if (dtype == MVIT_BF16 && attention_bwd_tc_supported(a, &why)) return attention_bwd_tc(a, st);
+    MVIT_REQUIRE(impl != MVIT_IMPL_TCGEN05, "attention_bwd: tcgen05 path unavailable: %s", why);
+  }
+  dim3 grid((Lq + ABQ - 1) / ABQ, B * heads);
   const size_t smem = sizeof(AttnBwdSmem);
   static bool attr_set = false;
   if (!attr_set) {

@@ -359,7 +359,7 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool):
     return dw, db
 
 
-def attention_bwd(q, k, v, out, dout, lse, scale: float, add_q: bool):
+def attention_bwd(q, k, v, out, dout, lse, scale: float, add_q: bool, impl: int = IMPL_AUTO):
     """-> (dq, dk, dv) in q.dtype, shapes of q / k / v."""
     global launch_count
     _need_cuda(q, k, v, out, dout, lse)
@@ -368,11 +368,15 @@ def attention_bwd(q, k, v, out, dout, lse, scale: float, add_q: bool):
     Lk = k.shape[2]
     dq = torch.empty_like(q)
     dkv = torch.zeros((2, B, h, Lk, d), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    ws = None
+    if q.dtype == torch.bfloat16 and impl != IMPL_SIMT:
+        ws = torch.empty((lib.mvit_attention_bwd_workspace_floats(B, h, Lq),), dtype=torch.float32, device=q.device)
     with _Timed("attention_bwd", 10.0 * B * h * Lq * Lk * d):
-        check(_lib.load().mvit_attention_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dq),
-                                             _ptr(dkv[0]), _ptr(dkv[1]), B, h, Lq, Lk, d, float(scale), 1 if add_q else 0,
-                                             _dt(q), _stream()), "mvit_attention_bwd")
-    launch_count += 1
+        check(lib.mvit_attention_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dq), _ptr(dkv[0]),
+                                     _ptr(dkv[1]), _ptr(ws), B, h, Lq, Lk, d, float(scale), 1 if add_q else 0, _dt(q),
+                                     impl, _stream()), "mvit_attention_bwd")
+    launch_count += 3 if ws is not None else 1
     return dq, dkv[0].to(q.dtype), dkv[1].to(q.dtype)
 
 

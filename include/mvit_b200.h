@@ -187,10 +187,13 @@ int mvit_linear_wgrad(const void *dy, const void *x, float *dw, float *db, int64
 
 /* Backward of mvit_attention_fwd (attention.py:267-279).  q/k/v/out as in the forward, dout [B, Lq, heads*d],
  * lse from the forward; dq [B, heads, Lq, d] (dtype, overwritten; includes the +q residual path),
- * dk/dv [B, heads, Lk, d] fp32, caller-zeroed, accumulated. */
+ * dk/dv [B, heads, Lk, d] fp32, caller-zeroed, accumulated.  workspace: fp32 scratch of
+ * mvit_attention_bwd_workspace_floats(B, heads, Lq) elements (16-byte aligned) for the tcgen05 path
+ * (bf16: three launches - row statistics, dQ, dK/dV - no [Lq, Lk] matrix in memory); NULL selects CUDA cores. */
+size_t mvit_attention_bwd_workspace_floats(int B, int heads, int Lq);
 int mvit_attention_bwd(const void *q, const void *k, const void *v, const void *out, const void *dout,
-                       const float *lse, void *dq, float *dk, float *dv, int B, int heads, int Lq, int Lk,
-                       int d, float scale, int add_q_residual, int dtype, void *stream);
+                       const float *lse, void *dq, float *dk, float *dv, float *workspace, int B, int heads,
+                       int Lq, int Lk, int d, float scale, int add_q_residual, int dtype, int impl, void *stream);
 
 /* Backward pieces of mvit_attention_pool_fwd (attention.py:12-83), geometry arguments as in the forward
  * (padding = kernel/2, no cls token):

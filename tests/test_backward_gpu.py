@@ -100,7 +100,8 @@ def test_linear_bwd(shape, epi, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
-@pytest.mark.parametrize("B,h,Lq,Lk,add_q", [(2, 2, 200, 72, True), (1, 3, 65, 130, False), (1, 1, 1024, 64, True)])
+@pytest.mark.parametrize("B,h,Lq,Lk,add_q", [(2, 2, 200, 72, True), (1, 3, 65, 130, False), (1, 1, 1024, 64, True),
+                                                 (1, 2, 784, 784, True), (2, 1, 3000, 784, True), (1, 1, 257, 300, False)])
 def test_attention_bwd(B, h, Lq, Lk, add_q, dtype):
     d = 96
     q, k, v, do = (synth_tensor(3, n, s) for n, s in (("q", (B, h, Lq, d)), ("k", (B, h, Lk, d)), ("v", (B, h, Lk, d)),
