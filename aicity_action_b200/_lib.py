@@ -39,7 +39,7 @@ SIGNATURES = {
     "mvit_preprocess_u8_fwd": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _p]),
     "mvit_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "mvit_gelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p]),
-    "mvit_linear_wgrad": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p]),
+    "mvit_linear_wgrad": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "mvit_attention_bwd_workspace_floats": (C.c_size_t, [_i, _i, _i]),
     "mvit_attention_bwd": (_i, [_p] * 10 + [_i] * 5 + [_f, _i, _i, _i, _p]),
     "mvit_attention_pool_bwd": (_i, [_i, _p, _i64, _i64, _i64, _p, _p, _p, _p] + [_i] * 13 + [_p]),

@@ -5,6 +5,7 @@
 // dgrad GEMMs already run on the forward tcgen05 kernel (dx = dy · W is a Linear with the transposed weight).
 #include "attention.cuh"
 #include "common.cuh"
+#include "linear.cuh"
 
 namespace mvit {
 
@@ -412,11 +413,17 @@ extern "C" int mvit_gelu_bwd(const void *pre, const void *dy, void *dpre, int64_
 }
 
 extern "C" int mvit_linear_wgrad(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int dtype,
-                                 void *stream) {
+                                 int impl, void *stream) {
   MVIT_REQUIRE(dy && x && dw, "linear_wgrad: null pointer");
   MVIT_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_wgrad: bad shape");
   MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "linear_wgrad: unknown dtype");
   if (M == 0) return 0;
+  if (impl != MVIT_IMPL_SIMT) {
+    const char *why = "fp32 runs on CUDA cores";
+    if (dtype == MVIT_BF16 && linear_wgrad_tc_supported(dy, x, dw, M, N, K, &why))
+      return linear_wgrad_tc(dy, x, dw, db, M, N, K, static_cast<cudaStream_t>(stream));
+    MVIT_REQUIRE(impl != MVIT_IMPL_TCGEN05, "linear_wgrad: tcgen05 path unavailable: %s", why);
+  }
   const int gx = (N + WT - 1) / WT, gy = (K + WT - 1) / WT;
   int splits = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * num_sms()) / (gx * gy)), (M + 255) / 256);
   splits = std::max(1, std::min(splits, 65535));

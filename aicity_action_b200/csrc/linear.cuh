@@ -19,4 +19,8 @@ bool linear_tc_supported(const LinearArgs &a, const char **why);
 int patch_conv_tc(const void *folded, const void *wf, const float *bias, const void *pos, void *out, int B, int Tf,
                   int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N, cudaStream_t st);
 
+// weight / bias gradient on tcgen05 (gemm_wgrad_tc.cu), bf16 only: dw[N,K] += dy^T x, db[N] += colsum(dy)
+int linear_wgrad_tc(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, cudaStream_t st);
+bool linear_wgrad_tc_supported(const void *dy, const void *x, const float *dw, int64_t M, int N, int K, const char **why);
+
 }  // namespace mvit

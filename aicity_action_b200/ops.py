@@ -342,7 +342,7 @@ def gelu_bwd(pre: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool):
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool, impl: int = IMPL_AUTO):
     """dy [..., N], x [..., K] -> (dw fp32 [N, K], db fp32 [N] | None)."""
     global launch_count
     _need_cuda(dy, x)
@@ -353,9 +353,9 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool):
     dw = torch.zeros((N, K), dtype=torch.float32, device=x.device)
     db = torch.zeros((N,), dtype=torch.float32, device=x.device) if want_bias else None
     with _Timed("linear_wgrad", 2.0 * M * N * K):
-        check(_lib.load().mvit_linear_wgrad(_ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, _dt(x), _stream()),
+        check(_lib.load().mvit_linear_wgrad(_ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, _dt(x), impl, _stream()),
               "mvit_linear_wgrad")
-    launch_count += 1
+    launch_count += 2 if (want_bias and x.dtype == torch.bfloat16) else 1
     return dw, db
 
 

@@ -181,9 +181,10 @@ int mvit_layernorm_bwd(const void *x, const float *gamma, const void *dy, void *
 int mvit_gelu_bwd(const void *pre, const void *dy, void *dpre, int64_t n, int dtype, void *stream);
 
 /* nn.Linear parameter gradients: dw[N,K] += dy[M,N]^T x[M,K];  db[N] += column sums of dy (db may be NULL).
- * (the input gradient dx = dy . W is mvit_linear_fwd with the transposed weight) */
+ * (the input gradient dx = dy . W is mvit_linear_fwd with the transposed weight).  bf16 runs on tcgen05 with both
+ * operands consumed MN-major straight from the row-major activations (no transposed copies), split over tokens. */
 int mvit_linear_wgrad(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int dtype,
-                      void *stream);
+                      int impl, void *stream);
 
 /* Backward of mvit_attention_fwd (attention.py:267-279).  q/k/v/out as in the forward, dout [B, Lq, heads*d],
  * lse from the forward; dq [B, heads, Lq, d] (dtype, overwritten; includes the +q residual path),

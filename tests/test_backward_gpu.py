@@ -99,6 +99,19 @@ def test_linear_bwd(shape, epi, dtype):
         check("dres", rc.grad, rr.grad, tol)
 
 
+@pytest.mark.parametrize("M,N,K", [(5000, 288, 96), (3001, 96, 384), (700, 768, 3072), (4096, 96, 448), (130, 1152, 384),
+                                   (64, 8, 8)], ids=str)
+def test_linear_wgrad_tensor_core(M, N, K):
+    """tcgen05 weight gradient (both operands MN-major, split over tokens) vs fp32 matmul of the same bf16 values."""
+    dy, x = synth_tensor(6, "dy", (M, N)).bfloat16(), synth_tensor(6, "x", (M, K)).bfloat16()
+    dw, db = ops.linear_wgrad(dy.cuda(), x.cuda(), True)
+    ref_w, ref_b = dy.float().t() @ x.float(), dy.float().sum(0)
+    check("dw", dw, ref_w, 1e-3)
+    check("db", db, ref_b, 1e-3)
+    dw2, _ = ops.linear_wgrad(dy.cuda(), x.cuda(), False, impl=ops.IMPL_SIMT)
+    check("dw(simt)", dw2, ref_w, 1e-3)
+
+
 @pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
 @pytest.mark.parametrize("B,h,Lq,Lk,add_q", [(2, 2, 200, 72, True), (1, 3, 65, 130, False), (1, 1, 1024, 64, True),
                                                  (1, 2, 784, 784, True), (2, 1, 3000, 784, True), (1, 1, 257, 300, False)])
