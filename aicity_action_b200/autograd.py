@@ -175,8 +175,16 @@ class _PoolQKV(Function):
                 dy, dg, db = ops.layernorm_bwd(conv, g, dy, eps)
             dw = torch.zeros((d, kernel[0] * kernel[1] * kernel[2]), dtype=torch.float32, device=qkv.device)
             ops.attention_pool_bwd(1, x_view, strides, dy, None, None, dw, B, heads, d, thw, kernel, stride)
-            ops.attention_pool_bwd(0, None, strides, dy, w.reshape(d, -1), dqkv5[:, :, i], None, B, heads, d, thw, kernel,
-                                   stride)
+            if tuple(stride) == (1, 1, 1) and all(k % 2 == 1 for k in kernel):
+                # unit stride: the input gradient is the same depthwise convolution with the taps reversed -> the tuned
+                # forward kernel, reading dy and writing straight into the q/k/v slice of dqkv
+                Lo = dy.shape[2]
+                ops.attention_pool_strided(dy, 0, (heads * Lo * d, d, Lo * d), B, heads, d, thw, kernel, stride, "conv",
+                                           w.detach().reshape(d, -1).flip(1).contiguous(), None, None, 0.0, False,
+                                           dqkv5[:, :, i], strides)
+            else:
+                ops.attention_pool_bwd(0, None, strides, dy, w.reshape(d, -1), dqkv5[:, :, i], None, B, heads, d, thw,
+                                       kernel, stride)
             grads += [_like_param(dw, w), _like_param(dg, g), _like_param(db, b)]
         return (dqkv, None, None, None, *grads)
 

@@ -6,6 +6,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "linear.cuh"
+#include "pool.cuh"
 
 namespace mvit {
 
@@ -53,16 +54,132 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T *__restrict_
   }
 }
 
+// Tuned form for even C <= 64*NP: lane owns the channel pairs {lane + 32 i}; the row's x / dy stay in registers across
+// the three passes, dgamma / dbeta partial sums stay in registers across ALL rows of the warp (grid-stride), and only
+// one shared-memory + one global atomic per channel is issued per CTA.
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  __device__ __forceinline__ static float2 load(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+  __device__ __forceinline__ static void store(float *p, float2 v) { *reinterpret_cast<float2 *>(p) = v; }
+};
+template <> struct Pair<bf16> {
+  __device__ __forceinline__ static float2 load(const bf16 *p) {
+    const uint32_t u = *reinterpret_cast<const uint32_t *>(p);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
+  __device__ __forceinline__ static void store(bf16 *p, float2 v) {
+    *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(v.x, v.y);
+  }
+};
+
+template <typename T, int NP>
+__global__ void __launch_bounds__(256) layernorm_bwd_pairs_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
+                                                                  const T *__restrict__ dy, T *__restrict__ dx,
+                                                                  float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                                  int64_t rows, int C, float eps) {
+  extern __shared__ float sm[];          // gamma[C] | dgamma[C] | dbeta[C]
+  float *s_g = sm, *sg = sm + C, *sb = sm + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_g[c] = gamma[c]; sg[c] = 0.f; sb[c] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, half = C >> 1;
+  const float invC = 1.0f / C;
+  float2 g[NP], adg[NP], adb[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int c2 = lane + 32 * i;
+    g[i] = c2 < half ? make_float2(s_g[2 * c2], s_g[2 * c2 + 1]) : make_float2(0.f, 0.f);
+    adg[i] = make_float2(0.f, 0.f);
+    adb[i] = make_float2(0.f, 0.f);
+  }
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += wstride) {
+    const T *px = x + r * C, *pdy = dy + r * C;
+    float2 xv[NP], dv[NP];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int c2 = lane + 32 * i;
+      if (c2 < half) {
+        xv[i] = Pair<T>::load(px + 2 * c2);
+        dv[i] = Pair<T>::load(pdy + 2 * c2);
+      } else {
+        xv[i] = make_float2(0.f, 0.f);
+        dv[i] = make_float2(0.f, 0.f);
+      }
+      s += xv[i].x + xv[i].y;
+    }
+    const float mean = warp_sum(s) * invC;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int c2 = lane + 32 * i;
+      if (c2 < half) {
+        xv[i].x -= mean; xv[i].y -= mean;
+        ss = fmaf(xv[i].x, xv[i].x, fmaf(xv[i].y, xv[i].y, ss));
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      xv[i].x *= rstd; xv[i].y *= rstd;                       // xhat (zero in unused slots)
+      const float gx = g[i].x * dv[i].x, gy = g[i].y * dv[i].y;
+      a += gx + gy;
+      b = fmaf(gx, xv[i].x, fmaf(gy, xv[i].y, b));
+      adg[i].x = fmaf(dv[i].x, xv[i].x, adg[i].x); adg[i].y = fmaf(dv[i].y, xv[i].y, adg[i].y);
+      adb[i].x += dv[i].x; adb[i].y += dv[i].y;
+    }
+    a = warp_sum(a) * invC;
+    b = warp_sum(b) * invC;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int c2 = lane + 32 * i;
+      if (c2 < half)
+        Pair<T>::store(dx + r * C + 2 * c2, make_float2(rstd * (g[i].x * dv[i].x - a - xv[i].x * b),
+                                                        rstd * (g[i].y * dv[i].y - a - xv[i].y * b)));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int c2 = lane + 32 * i;
+    if (c2 < half) {
+      atomicAdd(&sg[2 * c2], adg[i].x); atomicAdd(&sg[2 * c2 + 1], adg[i].y);
+      atomicAdd(&sb[2 * c2], adb[i].x); atomicAdd(&sb[2 * c2 + 1], adb[i].y);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sg[c]);
+    atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GELU backward
 // dpre = dy * d/dx[ x * Phi(x) ] = dy * (Phi(x) + x * phi(x)),  exact erf form (common.py:20 nn.GELU)
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
 template <typename T>
 __global__ void gelu_bwd_kernel(const T *__restrict__ pre, const T *__restrict__ dy, T *__restrict__ dpre, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float x = to_f32(pre[i]);
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-    dpre[i] = from_f32<T>(to_f32(dy[i]) * (cdf + x * pdf));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dpre[i] = from_f32<T>(to_f32(dy[i]) * gelu_grad(to_f32(pre[i])));
+}
+// 16-byte vectors (n a multiple of the vector width, aligned pointers)
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_bwd_vec_kernel(const T *__restrict__ pre, const T *__restrict__ dy,
+                                                           T *__restrict__ dpre, int64_t nvec) {
+  constexpr int W = Vec16<T>::N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float a[W], g[W];
+    Vec16<T>::load(pre + i * W, a);
+    Vec16<T>::load(dy + i * W, g);
+#pragma unroll
+    for (int e = 0; e < W; ++e) a[e] = g[e] * gelu_grad(a[e]);
+    Vec16<T>::store(dpre + i * W, a);
   }
 }
 
@@ -251,8 +368,8 @@ __global__ void __launch_bounds__(256) pool_conv_dgrad_kernel(const T *__restric
   const int lane = threadIdx.x & 31;
   const int L = p.T * p.H * p.W, Lo = p.To * p.Ho * p.Wo;
   const int64_t total = (int64_t)p.B * L * p.heads;
-  const int64_t o = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= total) return;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t o = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); o < total; o += wstride) {
   const int head = (int)(o % p.heads);
   const int64_t bl = o / p.heads;
   const int l = (int)(bl % L), b = (int)(bl / L);
@@ -261,22 +378,26 @@ __global__ void __launch_bounds__(256) pool_conv_dgrad_kernel(const T *__restric
 #pragma unroll
   for (int j = 0; j < NC; ++j) acc[j] = 0.f;
   const T *dyb = dy + ((int64_t)(b * p.heads + head) * Lo) * p.d;
-  for (int a = 0; a < p.kt; ++a) {
-    const int tn = t + p.pt - a;
-    if (tn < 0 || tn % p.st) continue;
-    const int to = tn / p.st;
-    if (to >= p.To) continue;
-    for (int bq = 0; bq < p.kh; ++bq) {
-      const int hn = h + p.ph - bq;
-      if (hn < 0 || hn % p.sh) continue;
-      const int ho = hn / p.sh;
-      if (ho >= p.Ho) continue;
-      for (int c = 0; c < p.kw; ++c) {
-        const int wn = w + p.pw - c;
-        if (wn < 0 || wn % p.sw) continue;
-        const int wo = wn / p.sw;
-        if (wo >= p.Wo) continue;
-        const T *pdy = dyb + (int64_t)((to * p.Ho + ho) * p.Wo + wo) * p.d;
+  // output index feeding this input position through tap a / bq / c of each axis (or -1): 9 divisions per position
+  int tv[3], hv[3], wv[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int tn = t + p.pt - a, hn = h + p.ph - a, wn = w + p.pw - a;
+    const int tq = tn / p.st, hq = hn / p.sh, wq = wn / p.sw;
+    tv[a] = (a < p.kt && tn >= 0 && tq * p.st == tn && tq < p.To) ? tq : -1;
+    hv[a] = (a < p.kh && hn >= 0 && hq * p.sh == hn && hq < p.Ho) ? hq : -1;
+    wv[a] = (a < p.kw && wn >= 0 && wq * p.sw == wn && wq < p.Wo) ? wq : -1;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (tv[a] < 0) continue;
+#pragma unroll
+    for (int bq = 0; bq < 3; ++bq) {
+      if (hv[bq] < 0) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (wv[c] < 0) continue;
+        const T *pdy = dyb + (int64_t)((tv[a] * p.Ho + hv[bq]) * p.Wo + wv[c]) * p.d;
         const float *pw = w_s + ((a * p.kh + bq) * p.kw + c) * p.d;
 #pragma unroll
         for (int j = 0; j < NC; ++j) acc[j] = fmaf(to_f32(pdy[lane + 32 * j]), pw[lane + 32 * j], acc[j]);
@@ -286,6 +407,71 @@ __global__ void __launch_bounds__(256) pool_conv_dgrad_kernel(const T *__restric
   T *dst = dx + b * p.x_bs + (int64_t)l * p.x_ls + head * p.x_hs;
 #pragma unroll
   for (int j = 0; j < NC; ++j) dst[lane + 32 * j] = from_f32<T>(acc[j]);
+  }
+}
+
+// Vectorised form of the same gather: thread = (input token*head, 16-byte channel group), so the index arithmetic is
+// amortised over 8 (bf16) / 4 (fp32) channels and dy is read with 16-byte loads.  Needs 16-byte aligned rows.
+template <typename T>
+__global__ void __launch_bounds__(256) pool_conv_dgrad_vec_kernel(const T *__restrict__ dy, const float *__restrict__ weight,
+                                                                  T *__restrict__ dx, PoolBwdParams p) {
+  constexpr int N = Vec16<T>::N;
+  extern __shared__ __align__(16) float w_s[];       // [taps][d]
+  const int taps = p.kt * p.kh * p.kw;
+  for (int i = threadIdx.x; i < taps * p.d; i += blockDim.x) {
+    const int tap = i / p.d, c = i - tap * p.d;
+    w_s[i] = weight[c * taps + tap];
+  }
+  __syncthreads();
+  const int groups = p.d / N;
+  const int L = p.T * p.H * p.W, Lo = p.To * p.Ho * p.Wo;
+  const int64_t total = (int64_t)p.B * L * p.heads * groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int g = (int)(i % groups);
+    const int64_t o = i / groups;
+    const int head = (int)(o % p.heads);
+    const int64_t bl = o / p.heads;
+    const int l = (int)(bl % L), b = (int)(bl / L);
+    const int w = l % p.W, h = (l / p.W) % p.H, t = l / (p.W * p.H);
+    int tv[3], hv[3], wv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int tn = t + p.pt - a, hn = h + p.ph - a, wn = w + p.pw - a;
+      const int tq = tn / p.st, hq = hn / p.sh, wq = wn / p.sw;
+      tv[a] = (a < p.kt && tn >= 0 && tq * p.st == tn && tq < p.To) ? tq : -1;
+      hv[a] = (a < p.kh && hn >= 0 && hq * p.sh == hn && hq < p.Ho) ? hq : -1;
+      wv[a] = (a < p.kw && wn >= 0 && wq * p.sw == wn && wq < p.Wo) ? wq : -1;
+    }
+    float acc[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) acc[e] = 0.f;
+    const T *dyb = dy + ((int64_t)(b * p.heads + head) * Lo) * p.d + g * N;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (tv[a] < 0) continue;
+#pragma unroll
+      for (int bq = 0; bq < 3; ++bq) {
+        if (hv[bq] < 0) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (wv[c] < 0) continue;
+          float v[N];
+          Vec16<T>::load(dyb + (int64_t)((tv[a] * p.Ho + hv[bq]) * p.Wo + wv[c]) * p.d, v);
+          const float *pw = w_s + ((a * p.kh + bq) * p.kw + c) * p.d + g * N;
+#pragma unroll
+          for (int e = 0; e < N; e += 4) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(pw + e);
+            acc[e] = fmaf(v[e], w4.x, acc[e]);
+            acc[e + 1] = fmaf(v[e + 1], w4.y, acc[e + 1]);
+            acc[e + 2] = fmaf(v[e + 2], w4.z, acc[e + 2]);
+            acc[e + 3] = fmaf(v[e + 3], w4.w, acc[e + 3]);
+          }
+        }
+      }
+    }
+    Vec16<T>::store(dx + b * p.x_bs + (int64_t)l * p.x_ls + head * p.x_hs + g * N, acc);
+  }
 }
 
 // conv weight gradient: dW[c][tap] += sum over (b, head, output position) x[input(tap)] * dy.  One warp per output
@@ -388,10 +574,30 @@ extern "C" int mvit_layernorm_bwd(const void *x, const float *gamma, const void 
   MVIT_REQUIRE(rows >= 0 && channels > 0 && channels <= 4096, "layernorm_bwd: bad shape");
   MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "layernorm_bwd: unknown dtype");
   if (rows == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 7) == 0;
+  if (channels % 2 == 0 && channels <= 768 && aligned) {
+    const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 8);
+    const size_t smem3 = 3 * (size_t)channels * sizeof(float);
+#define LN_BWD_PAIRS(T, NP)                                                                                            \
+  layernorm_bwd_pairs_kernel<T, NP><<<blocks, 256, smem3, st>>>(static_cast<const T *>(x), gamma, static_cast<const T *>(dy), \
+                                                                static_cast<T *>(dx), dgamma, dbeta, rows, channels, eps)
+    if (dtype == MVIT_F32) {
+      if (channels <= 128) LN_BWD_PAIRS(float, 2);
+      else if (channels <= 384) LN_BWD_PAIRS(float, 6);
+      else LN_BWD_PAIRS(float, 12);
+    } else {
+      if (channels <= 128) LN_BWD_PAIRS(bf16, 2);
+      else if (channels <= 384) LN_BWD_PAIRS(bf16, 6);
+      else LN_BWD_PAIRS(bf16, 12);
+    }
+#undef LN_BWD_PAIRS
+    MVIT_LAUNCH_OK("layernorm_bwd");
+    return 0;
+  }
   const int rows_per_cta = 64;
   const unsigned blocks = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
   const size_t smem = 2 * (size_t)channels * sizeof(float);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == MVIT_F32)
     layernorm_bwd_kernel<float><<<blocks, 256, smem, st>>>(static_cast<const float *>(x), gamma, static_cast<const float *>(dy), static_cast<float *>(dx), dgamma, dbeta, rows, channels, eps, rows_per_cta);
   else
@@ -404,8 +610,18 @@ extern "C" int mvit_gelu_bwd(const void *pre, const void *dy, void *dpre, int64_
   MVIT_REQUIRE(pre && dy && dpre && n >= 0, "gelu_bwd: bad arguments");
   MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "gelu_bwd: unknown dtype");
   if (n == 0) return 0;
-  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vw = dtype == MVIT_F32 ? 4 : 8;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dpre)) & 15) == 0;
+  if (aligned && n % vw == 0) {
+    const int64_t nvec = n / vw;
+    const unsigned vblocks = (unsigned)std::min<int64_t>((nvec + 255) / 256, (int64_t)num_sms() * 16);
+    if (dtype == MVIT_F32) gelu_bwd_vec_kernel<float><<<vblocks, 256, 0, st>>>(static_cast<const float *>(pre), static_cast<const float *>(dy), static_cast<float *>(dpre), nvec);
+    else gelu_bwd_vec_kernel<bf16><<<vblocks, 256, 0, st>>>(static_cast<const bf16 *>(pre), static_cast<const bf16 *>(dy), static_cast<bf16 *>(dpre), nvec);
+    MVIT_LAUNCH_OK("gelu_bwd");
+    return 0;
+  }
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == MVIT_F32) gelu_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(pre), static_cast<const float *>(dy), static_cast<float *>(dpre), n);
   else gelu_bwd_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16 *>(pre), static_cast<const bf16 *>(dy), static_cast<bf16 *>(dpre), n);
   MVIT_LAUNCH_OK("gelu_bwd");
@@ -480,10 +696,17 @@ static int pool_bwd_dispatch(int what, const void *x, const void *dy, const floa
   const int nc = p.d / 32;
   const int Lo = p.To * p.Ho * p.Wo, L = p.T * p.H * p.W;
   const size_t wsm = (size_t)p.kt * p.kh * p.kw * p.d * sizeof(float);
+  const int64_t vb = 16 / (int64_t)sizeof(T);
+  const bool vec_ok = what == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 &&
+                      p.x_bs % vb == 0 && p.x_ls % vb == 0 && p.x_hs % vb == 0 && p.d % vb == 0;
 #define POOL_BWD_CASE(NC)                                                                                             \
   case NC:                                                                                                            \
-    if (what == 0) {                                                                                                  \
-      const int64_t blocks = ((int64_t)p.B * L * p.heads + 7) / 8;                                                    \
+    if (what == 0 && vec_ok) {                                                                                        \
+      const int64_t items = (int64_t)p.B * L * p.heads * (p.d / Vec16<T>::N);                                         \
+      const int64_t blocks = std::min<int64_t>((items + 255) / 256, (int64_t)num_sms() * 16);                         \
+      pool_conv_dgrad_vec_kernel<T><<<(unsigned)blocks, 256, wsm, st>>>(static_cast<const T *>(dy), weight, static_cast<T *>(dx), p); \
+    } else if (what == 0) {                                                                                           \
+      const int64_t blocks = std::min<int64_t>(((int64_t)p.B * L * p.heads + 7) / 8, (int64_t)num_sms() * 16);       \
       pool_conv_dgrad_kernel<T, NC><<<(unsigned)blocks, 256, wsm, st>>>(static_cast<const T *>(dy), weight, static_cast<T *>(dx), p); \
     } else if (what == 1) {                                                                                           \
       const int opw = 64;                                                                                             \
@@ -525,6 +748,15 @@ extern "C" int mvit_attention_pool_bwd(int what, const void *x, int64_t x_bs, in
   p.pt = kt / 2; p.ph = kh / 2; p.pw = kw / 2;
   p.To = (T + 2 * p.pt - kt) / st + 1; p.Ho = (H + 2 * p.ph - kh) / sh + 1; p.Wo = (W + 2 * p.pw - kw) / sw + 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (what == 1) {
+    PoolParams q{};
+    q.in_bs = x_bs; q.in_ls = x_ls; q.in_hs = x_hs;
+    q.B = B; q.heads = heads; q.d = d; q.T = T; q.H = H; q.W = W;
+    q.kt = kt; q.kh = kh; q.kw = kw; q.st = st; q.sh = sh; q.sw = sw;
+    q.pt = p.pt; q.ph = p.ph; q.pw = p.pw; q.To = p.To; q.Ho = p.Ho; q.Wo = p.Wo;
+    const int r = pool_wgrad_tiled_try(x, dy, dw, q, dtype, s);
+    if (r <= 0) return r;
+  }
   if (dtype == MVIT_F32) return pool_bwd_dispatch<float>(what, x, dy, weight, dx, dw, p, s);
   return pool_bwd_dispatch<bf16>(what, x, dy, weight, dx, dw, p, s);
 }

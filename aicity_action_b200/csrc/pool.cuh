@@ -14,4 +14,7 @@ struct PoolParams {
 int pool_tiled_try(const void *in, const float *w, const float *g, const float *b, void *out,
                    const PoolParams &p, int mode, int dtype, cudaStream_t st);
 
+// tuned conv weight gradient (pool_bwd_tiled.cu): dw[96, 27] += ; dy is [B, heads, L', 96] contiguous; same return codes
+int pool_wgrad_tiled_try(const void *in, const void *dy, float *dw, const PoolParams &p, int dtype, cudaStream_t st);
+
 }  // namespace mvit

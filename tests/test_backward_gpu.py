@@ -135,7 +135,10 @@ def test_attention_bwd(B, h, Lq, Lk, add_q, dtype):
 @pytest.mark.parametrize("thw,sq,skv,heads,pool_q", [((4, 8, 8), (1, 1, 1), (1, 2, 2), 2, True),
                                                       ((4, 8, 8), (1, 2, 2), (1, 4, 4), 1, True),
                                                       ((3, 7, 5), (2, 2, 2), (1, 2, 2), 2, True),
-                                                      ((4, 8, 8), None, (1, 2, 2), 2, False)], ids=str)
+                                                      ((4, 8, 8), None, (1, 2, 2), 2, False),
+                                                      ((2, 16, 16), (1, 1, 1), (1, 8, 8), 1, True),
+                                                      ((3, 13, 11), (1, 1, 1), (1, 2, 2), 2, True),
+                                                      ((5, 9, 18), (1, 2, 2), (1, 4, 4), 1, True)], ids=str)
 def test_pool_qkv_bwd(thw, sq, skv, heads, pool_q, dtype):
     d, B = 96, 2
     N = thw[0] * thw[1] * thw[2]
