@@ -257,10 +257,43 @@ def run_ours(args):
         barrier()
         ms_e2e = t0.elapsed_time(t1)
 
-    times = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- secondary figure: one training step (forward + backward + AdamW) of the same model on the same clips, bf16
+    # autocast as TRAIN.MIXED_PRECISION does, DistributedDataParallel over NCCL when world > 1 (build.py:44-53)
+    ms_train, train_launches, train_steps = 0.0, 0, 0
+    if not args.no_train:
+        import torch.nn.functional as F
+        model.train()
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=0.05)
+        labels = torch.randint(0, cfg.MODEL.NUM_CLASSES, (B,), device=dev)
+        train_steps = max(2, min(K, 5))
+
+        def train_step():
+            loss = F.cross_entropy(net([dev_clip]).float(), labels)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(2):
+            train_step()
+        barrier()
+        n0 = ops.launch_count
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(train_steps):
+            loss = train_step()
+        r1.record()
+        barrier()
+        ms_train = r0.elapsed_time(r1)
+        train_launches = ops.launch_count - n0
+        assert torch.isfinite(loss)
+        model.eval()
+
+    times = torch.tensor([ms, ms_e2e, ms_train], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = times.tolist()
+    ms, ms_e2e, ms_train = times.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -289,6 +322,12 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roofline, "kernels": kernels, "clocks": clocks,
     }
+    if train_steps:
+        line["train"] = {"value": world * B * train_steps / (ms_train * 1e-3), "unit": "clips/s",
+                         "ms_per_step": ms_train / train_steps, "steps": train_steps, "batch_per_gpu": B,
+                         "gpu_launches": train_launches,
+                         "what": "forward + backward + AdamW step, bf16 activations / fp32 master weights"
+                                 + (", DDP gradient all-reduce over NCCL" if world > 1 else "")}
     if world == 1 and not args.no_cpu_baseline:
         v, cores, cpu_ms = cpu_port_clips_per_s(steps=2, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
@@ -307,6 +346,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
