@@ -72,7 +72,14 @@ template <> struct Pair<bf16> {
   }
 };
 
-template <typename T, int NP>
+template <int LPR> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LPR lanes share one row (16: two rows per warp, for C = 96; 32 otherwise); lane `sub` owns channel pairs {sub + LPR i}.
+template <typename T, int NP, int LPR>
 __global__ void __launch_bounds__(256) layernorm_bwd_pairs_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
                                                                   const T *__restrict__ dy, T *__restrict__ dx,
                                                                   float *__restrict__ dgamma, float *__restrict__ dbeta,
@@ -81,25 +88,29 @@ __global__ void __launch_bounds__(256) layernorm_bwd_pairs_kernel(const T *__res
   float *s_g = sm, *sg = sm + C, *sb = sm + 2 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) { s_g[c] = gamma[c]; sg[c] = 0.f; sb[c] = 0.f; }
   __syncthreads();
-  const int lane = threadIdx.x & 31, half = C >> 1;
+  constexpr int RPW = 32 / LPR;          // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane % LPR, half = C >> 1;
   const float invC = 1.0f / C;
   float2 g[NP], adg[NP], adb[NP];
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    const int c2 = lane + 32 * i;
+    const int c2 = sub + LPR * i;
     g[i] = c2 < half ? make_float2(s_g[2 * c2], s_g[2 * c2 + 1]) : make_float2(0.f, 0.f);
     adg[i] = make_float2(0.f, 0.f);
     adb[i] = make_float2(0.f, 0.f);
   }
-  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += wstride) {
+  const int64_t rstride = (int64_t)gridDim.x * (blockDim.x >> 5) * RPW;
+  // every lane of a warp runs the same number of iterations (shuffles are warp-wide); rows past the end are masked
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; r0 < rows; r0 += rstride) {
+    const int64_t r = r0 + lane / LPR;
+    const bool live = r < rows;
     const T *px = x + r * C, *pdy = dy + r * C;
     float2 xv[NP], dv[NP];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      const int c2 = lane + 32 * i;
-      if (c2 < half) {
+      const int c2 = sub + LPR * i;
+      if (live && c2 < half) {
         xv[i] = Pair<T>::load(px + 2 * c2);
         dv[i] = Pair<T>::load(pdy + 2 * c2);
       } else {
@@ -108,17 +119,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_pairs_kernel(const T *__res
       }
       s += xv[i].x + xv[i].y;
     }
-    const float mean = warp_sum(s) * invC;
+    const float mean = group_sum<LPR>(s) * invC;
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      const int c2 = lane + 32 * i;
+      const int c2 = sub + LPR * i;
       if (c2 < half) {
         xv[i].x -= mean; xv[i].y -= mean;
         ss = fmaf(xv[i].x, xv[i].x, fmaf(xv[i].y, xv[i].y, ss));
       }
     }
-    const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
+    const float rstd = rsqrtf(group_sum<LPR>(ss) * invC + eps);
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -129,19 +140,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_pairs_kernel(const T *__res
       adg[i].x = fmaf(dv[i].x, xv[i].x, adg[i].x); adg[i].y = fmaf(dv[i].y, xv[i].y, adg[i].y);
       adb[i].x += dv[i].x; adb[i].y += dv[i].y;
     }
-    a = warp_sum(a) * invC;
-    b = warp_sum(b) * invC;
+    a = group_sum<LPR>(a) * invC;
+    b = group_sum<LPR>(b) * invC;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      const int c2 = lane + 32 * i;
-      if (c2 < half)
+      const int c2 = sub + LPR * i;
+      if (live && c2 < half)
         Pair<T>::store(dx + r * C + 2 * c2, make_float2(rstd * (g[i].x * dv[i].x - a - xv[i].x * b),
                                                         rstd * (g[i].y * dv[i].y - a - xv[i].y * b)));
     }
   }
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    const int c2 = lane + 32 * i;
+    const int c2 = sub + LPR * i;
     if (c2 < half) {
       atomicAdd(&sg[2 * c2], adg[i].x); atomicAdd(&sg[2 * c2 + 1], adg[i].y);
       atomicAdd(&sb[2 * c2], adb[i].x); atomicAdd(&sb[2 * c2 + 1], adb[i].y);
@@ -577,19 +588,22 @@ extern "C" int mvit_layernorm_bwd(const void *x, const float *gamma, const void 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 7) == 0;
   if (channels % 2 == 0 && channels <= 768 && aligned) {
-    const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 8);
+    const unsigned blocks = (unsigned)std::min<int64_t>((rows + 15) / 16, (int64_t)num_sms() * 8);
     const size_t smem3 = 3 * (size_t)channels * sizeof(float);
-#define LN_BWD_PAIRS(T, NP)                                                                                            \
-  layernorm_bwd_pairs_kernel<T, NP><<<blocks, 256, smem3, st>>>(static_cast<const T *>(x), gamma, static_cast<const T *>(dy), \
-                                                                static_cast<T *>(dx), dgamma, dbeta, rows, channels, eps)
+#define LN_BWD_PAIRS(T, NP, LPR)                                                                                       \
+  layernorm_bwd_pairs_kernel<T, NP, LPR><<<blocks, 256, smem3, st>>>(static_cast<const T *>(x), gamma,                 \
+                                                                     static_cast<const T *>(dy), static_cast<T *>(dx), \
+                                                                     dgamma, dbeta, rows, channels, eps)
     if (dtype == MVIT_F32) {
-      if (channels <= 128) LN_BWD_PAIRS(float, 2);
-      else if (channels <= 384) LN_BWD_PAIRS(float, 6);
-      else LN_BWD_PAIRS(float, 12);
+      if (channels <= 96) LN_BWD_PAIRS(float, 3, 16);
+      else if (channels <= 192) LN_BWD_PAIRS(float, 3, 32);
+      else if (channels <= 384) LN_BWD_PAIRS(float, 6, 32);
+      else LN_BWD_PAIRS(float, 12, 32);
     } else {
-      if (channels <= 128) LN_BWD_PAIRS(bf16, 2);
-      else if (channels <= 384) LN_BWD_PAIRS(bf16, 6);
-      else LN_BWD_PAIRS(bf16, 12);
+      if (channels <= 96) LN_BWD_PAIRS(bf16, 3, 16);
+      else if (channels <= 192) LN_BWD_PAIRS(bf16, 3, 32);
+      else if (channels <= 384) LN_BWD_PAIRS(bf16, 6, 32);
+      else LN_BWD_PAIRS(bf16, 12, 32);
     }
 #undef LN_BWD_PAIRS
     MVIT_LAUNCH_OK("layernorm_bwd");

@@ -7,6 +7,8 @@
 // lane of warp 1 issues tcgen05.mma (M128 x N{128,192} x K16, four per chunk) into a TMEM accumulator, warps 4-7 add the
 // finished tile into dW with vector fp32 reductions.  CTAs of one token slice are adjacent in the grid so the
 // activation chunks they share are served by L2.
+// Bias gradient for free: every stage carries one extra, constant x-box whose feature 0 is 1.0; the CTAs of the first
+// feature tile run their MMAs 16 columns wider, so accumulator column BQ is sum_m dy[m, n] = db[n] - dy is not re-read.
 #include "linear.cuh"
 #include "tc_common.cuh"
 
@@ -20,8 +22,8 @@ constexpr int kThreads = 256;
 
 template <int BQ> struct Cfg {
   static constexpr int kABoxes = BP / kBox, kBBoxes = BQ / kBox;
-  static constexpr int kStageBytes = (kABoxes + kBBoxes) * kBoxBytes;
-  static constexpr int kStages = BQ == 192 ? 5 : 6;
+  static constexpr int kStageBytes = (kABoxes + kBBoxes + 1) * kBoxBytes;   // + the constant ones box
+  static constexpr int kStages = BQ == 192 ? 4 : 5;
   static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
   static constexpr uint32_t kTmemCols = 256;
 };
@@ -29,7 +31,8 @@ template <int BQ> struct Cfg {
 template <int BQ>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
-                       float *__restrict__ dw, int P, int Q, int64_t M, int64_t m_per_split, int q_tiles) {
+                       float *__restrict__ dw, float *__restrict__ db, int P, int Q, int64_t M, int64_t m_per_split,
+                       int q_tiles) {
   using C = Cfg<BQ>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,6 +61,18 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
     tmem_alloc(tmem_slot, C::kTmemCols);
     tmem_relinquish();
   }
+  const bool with_bias = db != nullptr && q0 == 0;     // this CTA also produces db[p0 .. p0+128)
+  if (warp == 3 && with_bias) {
+    // ones box of every stage: [64 tokens][64 features] bf16, 128B-swizzled, feature 0 = 1.0, the rest 0
+    for (int st = 0; st < C::kStages; ++st) {
+      uint4 *box = reinterpret_cast<uint4 *>(smem + st * C::kStageBytes + (C::kABoxes + C::kBBoxes) * kBoxBytes);
+      for (int i = lane; i < kBoxBytes / 16; i += 32) {
+        const int r = i >> 3, c16 = i & 7;             // token row, physical 16-byte slot
+        box[i] = make_uint4(c16 == (r & 7) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+      }
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -70,14 +85,15 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
       uint8_t *a = smem + s * C::kStageBytes, *b = a + C::kABoxes * kBoxBytes;
       // rows past M and columns past P / Q are zero-filled by TMA and contribute nothing
       const int m0 = (int)(m_begin + (int64_t)i * BMT);
-      mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+      mbar_arrive_expect_tx(&full[s], (C::kABoxes + C::kBBoxes) * kBoxBytes);
 #pragma unroll
       for (int c = 0; c < C::kABoxes; ++c) tma_load_2d(a + c * kBoxBytes, &tmap_dy, &full[s], p0 + c * kBox, m0);
 #pragma unroll
       for (int c = 0; c < C::kBBoxes; ++c) tma_load_2d(b + c * kBoxBytes, &tmap_x, &full[s], q0 + c * kBox, m0);
     }
   } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = make_idesc_bf16(BP, BQ, 1, 1);       // A and B both MN-major
+    // A and B both MN-major; 16 more columns (the ones box) when this CTA also reduces the bias gradient
+    const uint32_t idesc = with_bias ? make_idesc_bf16(BP, BQ + 16, 1, 1) : make_idesc_bf16(BP, BQ, 1, 1);
     const uint32_t base = smem_u32(smem);
     for (int i = 0; i < chunks; ++i) {
       const int s = i % C::kStages;
@@ -113,30 +129,16 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
         }
       }
     }
+    if (with_bias) {
+      uint32_t o[16];
+      tmem_ld16(taddr + BQ, o);
+      tmem_ld_wait();
+      if (prow < P) atomicAdd(&db[prow], __uint_as_float(o[0]));
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
-}
-
-// column sums of dy (the bias gradient): db[n] += sum_m dy[m, n].  Thread = 8 adjacent columns (16-byte loads).
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict__ dy, float *__restrict__ db, int64_t M,
-                                                          int N, int64_t rows_per_cta) {
-  const int groups = N / 8;                        // column groups of 8
-  const int gpb = min(groups, 256);                // groups handled per block pass
-  const int rows_par = 256 / gpb;                  // rows processed in parallel by one block
-  const int g = blockIdx.x * gpb + threadIdx.x % gpb, rl = threadIdx.x / gpb;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
-  if (g >= groups || rl >= rows_par) return;
-  float acc[8] = {};
-  for (int64_t r = r0 + rl; r < r1; r += rows_par) {
-    float f[8];
-    Vec16<bf16>::load(dy + r * N + g * 8, f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += f[e];
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) atomicAdd(&db[g * 8 + e], acc[e]);
 }
 
 }  // namespace wgrad
@@ -150,7 +152,7 @@ bool linear_wgrad_tc_supported(const void *dy, const void *x, const float *dw, i
 }
 
 template <int BQ>
-static int launch_wgrad(const void *dy, const void *x, float *dw, int64_t M, int N, int K, cudaStream_t st) {
+static int launch_wgrad(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, cudaStream_t st) {
   using C = wgrad::Cfg<BQ>;
   CUtensorMap tdy, tx;
   auto enc2 = [&](CUtensorMap *m, const void *ptr, uint64_t cols, uint64_t rows) {
@@ -175,22 +177,13 @@ static int launch_wgrad(const void *dy, const void *x, float *dw, int64_t M, int
   splits = (chunks + cps - 1) / cps;
   MVIT_REQUIRE(splits < 65536, "linear_wgrad: too many token splits");
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  wgrad::linear_wgrad_tc_kernel<BQ><<<grid, wgrad::kThreads, C::kSmemBytes, st>>>(tdy, tx, dw, N, K, M, cps * wgrad::BMT, q_tiles);
+  wgrad::linear_wgrad_tc_kernel<BQ><<<grid, wgrad::kThreads, C::kSmemBytes, st>>>(tdy, tx, dw, db, N, K, M, cps * wgrad::BMT, q_tiles);
   MVIT_LAUNCH_OK("linear_wgrad(tcgen05)");
   return 0;
 }
 
 int linear_wgrad_tc(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, cudaStream_t st) {
-  int r = K > 128 ? launch_wgrad<192>(dy, x, dw, M, N, K, st) : launch_wgrad<128>(dy, x, dw, M, N, K, st);
-  if (r) return r;
-  if (db) {
-    const int groups = N / 8, gpb = std::min(groups, 256);
-    const int64_t rows_per_cta = std::max<int64_t>(256, (M + 4 * num_sms() - 1) / (4 * num_sms()));
-    dim3 grid((unsigned)((groups + gpb - 1) / gpb), (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
-    wgrad::colsum_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const bf16 *>(dy), db, M, N, rows_per_cta);
-    MVIT_LAUNCH_OK("linear_wgrad(bias)");
-  }
-  return 0;
+  return K > 128 ? launch_wgrad<192>(dy, x, dw, db, M, N, K, st) : launch_wgrad<128>(dy, x, dw, db, M, N, K, st);
 }
 
 }  // namespace mvit

@@ -355,7 +355,7 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool, impl: int =
     with _Timed("linear_wgrad", 2.0 * M * N * K):
         check(_lib.load().mvit_linear_wgrad(_ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, _dt(x), impl, _stream()),
               "mvit_linear_wgrad")
-    launch_count += 2 if (want_bias and x.dtype == torch.bfloat16) else 1
+    launch_count += 1
     return dw, db
 
 
