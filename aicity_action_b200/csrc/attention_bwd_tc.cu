@@ -52,29 +52,33 @@ __global__ void __launch_bounds__(256) prep_kernel(const bf16 *__restrict__ q, c
                                                    const bf16 *__restrict__ dout, const float *__restrict__ lse,
                                                    float *__restrict__ delta, float *__restrict__ lse2, int heads, int Lq,
                                                    int Lq_pad, int add_q, int64_t total) {
-  const int lane = threadIdx.x & 31;
-  const int64_t idx = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (idx >= total) return;
-  const int bh = (int)(idx / Lq_pad), row = (int)(idx % Lq_pad);
-  if (row >= Lq) {
-    if (lane == 0) { delta[idx] = 0.f; lse2[idx] = 0.f; }
-    return;
-  }
-  const int b = bh / heads, head = bh % heads;
-  const int64_t o = (((int64_t)b * Lq + row) * heads + head) * D;
-  const bf16 *qr = q + ((int64_t)bh * Lq + row) * D;
+  // 16 lanes per row (12 of them active: 8 channels = one 16-byte load each), two rows per warp
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const int64_t idx = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+  const bool in_range = idx < total;
+  const int bh = in_range ? (int)(idx / Lq_pad) : 0, row = in_range ? (int)(idx % Lq_pad) : 0;
+  const bool live = in_range && row < Lq;
   float s = 0.f;
+  if (live && sub < 12) {
+    const int b = bh / heads, head = bh % heads;
+    const int64_t o = (((int64_t)b * Lq + row) * heads + head) * D + sub * 8;
+    float ov[8], gv[8];
+    Vec16<bf16>::load(out + o, ov);
+    Vec16<bf16>::load(dout + o, gv);
+    if (add_q) {
+      float qv[8];
+      Vec16<bf16>::load(q + ((int64_t)bh * Lq + row) * D + sub * 8, qv);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int ch = lane + 32 * c;
-    float ov = __bfloat162float(out[o + ch]);
-    if (add_q) ov -= __bfloat162float(qr[ch]);
-    s = fmaf(__bfloat162float(dout[o + ch]), ov, s);
+      for (int e = 0; e < 8; ++e) ov[e] -= qv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s = fmaf(gv[e], ov[e], s);
   }
-  s = warp_sum(s);
-  if (lane == 0) {
-    delta[idx] = s;
-    lse2[idx] = lse[(int64_t)bh * Lq + row] * kLog2e;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (in_range && sub == 0) {
+    delta[idx] = live ? s : 0.f;
+    lse2[idx] = live ? lse[(int64_t)bh * Lq + row] * kLog2e : 0.f;
   }
 }
 
@@ -540,7 +544,7 @@ int attention_bwd_tc(const AttnBwdArgs &a, cudaStream_t st) {
   float *delta = a.workspace, *lse2 = a.workspace + (size_t)BH * Lq_pad;
   {
     const int64_t total = (int64_t)BH * Lq_pad;
-    prep_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(static_cast<const bf16 *>(a.q), static_cast<const bf16 *>(a.out),
+    prep_kernel<<<(unsigned)((total + 15) / 16), 256, 0, st>>>(static_cast<const bf16 *>(a.q), static_cast<const bf16 *>(a.out),
                                                             static_cast<const bf16 *>(a.dout), a.lse, delta, lse2, a.heads,
                                                             a.Lq, Lq_pad, a.add_q, total);
     MVIT_LAUNCH_OK("attention_bwd(prep)");

@@ -9,7 +9,7 @@ from aicity_action_b200 import ops  # noqa: E402
 
 B = 8
 shapes = []
-for tokens, C, blocks in ((50176, 96, 2), (12544, 192, 3), (3136, 384, 16), (784, 768, 3)):
+for tokens, C, blocks in ((100352, 96, 1), (25088, 192, 3), (6272, 384, 16), (1568, 768, 3)):
     M = B * tokens
     shapes += [("qkv", M, 3 * C, C, blocks), ("proj", M, C, C, blocks), ("fc1", M, 4 * C, C, blocks),
                ("fc2", M, C, 4 * C, blocks)]
