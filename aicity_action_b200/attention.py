@@ -29,7 +29,10 @@ def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     if x.dtype == torch.bfloat16 or x.dtype == torch.uint8:     # uint8 = raw frames, normalised on the device
         return torch.bfloat16
     if x.dtype == torch.float32:
-        if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+        # any reduced-precision autocast region selects the tensor-core path; fp16 autocast (what the reference's
+        # `torch.cuda.amp.autocast(enabled=TRAIN.MIXED_PRECISION)` requests, train_net.py:126) is served in bf16:
+        # same 16-bit storage, wider exponent, so the GradScaler that accompanies it is harmless
+        if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") in (torch.bfloat16, torch.float16):
             return torch.bfloat16
         return torch.float32
     raise TypeError(f"unsupported activation dtype {x.dtype} (float32 or bfloat16)")
@@ -225,10 +228,13 @@ class MultiScaleAttention(nn.Module):
     def forward(self, x, thw_shape, residual=None, row_scale=None):
         """Reference contract: (x [B,N,dim], thw) -> (proj(attn) [B,Lq,dim_out], thw').
         `residual` / `row_scale` (used by MultiScaleBlock) fold `x_res + drop_path(.)` into the proj GEMM."""
-        if self.drop_rate > 0.0 and self.training:
-            raise NotImplementedError("proj dropout in training is not supported by the B200 path yet")
         dt = _compute_dtype(x)
         y, out_shape = self.attend(x.to(dt), thw_shape)
+        if self.drop_rate > 0.0 and self.training:
+            # MVIT.DROPOUT_RATE > 0 (0.0 in every shipped config): the dropout mask sits between the GEMM and the
+            # residual add, so the epilogue fusion is split and the elementwise tail is left to PyTorch
+            out = self.proj_drop(AG.linear(y, self.proj.weight, self.proj.bias))
+            return AG.scale_add(out, residual, row_scale), out_shape
         out = AG.linear(y, self.proj.weight, self.proj.bias, residual=residual, row_scale=row_scale)
         return out, out_shape
 

@@ -94,6 +94,13 @@ def linear(x, weight, bias=None, *, residual=None, row_scale=None, gelu=False):
     return ops.linear(x, cached_weight(weight, x.dtype), bias, residual=residual, row_scale=row_scale, gelu=gelu)
 
 
+def scale_add(y, residual=None, row_scale=None):
+    """residual + y * row_scale with plain tensor ops (only used when a dropout mask forbids the epilogue fusion)."""
+    if row_scale is not None:
+        y = y * row_scale.to(y.dtype).view(-1, *([1] * (y.ndim - 1)))
+    return y if residual is None else residual + y
+
+
 # ------------------------------------------------------------------------------------------------ attention
 class _Attention(Function):
     @staticmethod

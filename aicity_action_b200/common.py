@@ -55,6 +55,9 @@ class Mlp(nn.Module):
     def forward(self, x, residual=None, row_scale=None):
         """Returns fc2(gelu(fc1(x))) * row_scale + residual."""
         if self.drop_rate > 0.0 and self.training:
-            raise NotImplementedError("MVIT.DROPOUT_RATE > 0 in training is not supported by the B200 path yet")
+            # dropout after the activation and after fc2 (common.py:28-33): un-fused elementwise tail, see attention.py
+            h = self.drop(AG.linear(x, self.fc1.weight, self.fc1.bias, gelu=True))
+            y = self.drop(AG.linear(h, self.fc2.weight, self.fc2.bias))
+            return AG.scale_add(y, residual, row_scale)
         h = AG.linear(x, self.fc1.weight, self.fc1.bias, gelu=True)
         return AG.linear(h, self.fc2.weight, self.fc2.bias, residual=residual, row_scale=row_scale)

@@ -329,3 +329,35 @@ def test_inference_path_unchanged_by_autograd_routing():
     assert not p.requires_grad
     q = m([x])                       # grad mode on: same numbers, now differentiable
     assert q.requires_grad and rel_inf(q.detach(), p) < 2e-2
+
+
+def test_dropout_and_droppath_training_runs():
+    """MVIT.DROPOUT_RATE > 0 (un-fused dropout tail) and DropPath: a step runs, every gradient is finite, and in eval the
+    model is unchanged by the dropout modules."""
+    c = MODEL_CASES[0]
+    cfg = aicity_cfg(c["yaml"], tiny_cfg_overrides(c) + ["MVIT.DROPOUT_RATE", 0.1, "MVIT.DROPPATH_RATE", 0.3,
+                                                        "MODEL.DROPOUT_RATE", 0.5])
+    m = MViT(cfg).train()
+    load_synth(m, c["seed"])
+    m = m.cuda()
+    x = synth_clip(c["seed"], 4, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda()
+    torch.manual_seed(0)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.cross_entropy(m([x]).float(), torch.tensor([1, 2, 3, 4]).cuda())
+    loss.backward()
+    assert torch.isfinite(loss)
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_fp16_autocast_is_served_by_the_bf16_kernels():
+    c = MODEL_CASES[0]
+    cfg, m, _ = _train_model(c)
+    m.eval()
+    x = synth_clip(c["seed"], 2, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda()
+    with torch.no_grad():
+        with torch.autocast("cuda", dtype=torch.float16):
+            a = m([x])
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            b = m([x])
+    assert torch.equal(a, b)

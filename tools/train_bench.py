@@ -1,6 +1,9 @@
 """Training-step timing of the B200 path: forward + backward + AdamW on synthetic clips.
 
-    python tools/train_bench.py --batch 2 --size 448 --steps 5 [--fp32] [--checkpoint]
+    python tools/train_bench.py --batch 8 --size 448 --steps 5 [--fp32] [--no-checkpoint]
+
+Follows the reference's own training recipe (README.md:100-112): ACT_CHECKPOINT True, DROPPATH_RATE 0.4,
+head DROPOUT_RATE 0.5, AdamW(lr 1e-4, wd 1e-4, eps 1e-8), clip_grad_norm 1.0, cross-entropy on random labels.
 
 Prints one JSON line with ms/step, clips/s and the per-kernel-category device time (CUDA events on the launching stream).
 Under torchrun it wraps the model in DistributedDataParallel (NCCL gradient all-reduce, as build.py:44-53 does)."""
@@ -26,7 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--fp32", action="store_true")
-    ap.add_argument("--checkpoint", action="store_true")
+    ap.add_argument("--no-checkpoint", action="store_true", help="keep activations instead of MODEL.ACT_CHECKPOINT")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -35,13 +38,14 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl")
     yaml = "MVITV2_FULL_B_16x4_CONV_448.yaml" if a.size == 448 else "MVITV2_FULL_B_16x4_CONV.yaml"
-    cfg = aicity_cfg(yaml, ["MODEL.ACT_CHECKPOINT", bool(a.checkpoint)])
+    cfg = aicity_cfg(yaml, ["MODEL.ACT_CHECKPOINT", not a.no_checkpoint, "MVIT.DROPPATH_RATE", 0.4,
+                            "MODEL.DROPOUT_RATE", 0.5])
     torch.manual_seed(0)
     model = MViT(cfg).cuda().train()
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, eps=1e-8)
     g = torch.Generator(device="cuda").manual_seed(1 + rank)
     x = torch.randn((a.batch, 3, cfg.DATA.NUM_FRAMES, a.size, a.size), device="cuda", generator=g)
     y = torch.randint(0, cfg.MODEL.NUM_CLASSES, (a.batch,), device="cuda", generator=g)
@@ -52,6 +56,7 @@ def main():
         loss = F.cross_entropy(logits.float(), y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
 
@@ -78,7 +83,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "train_clips_per_sec", "value": round(a.batch * world / (ms.item() / 1e3), 2),
                           "ms_per_step": round(ms.item(), 2), "n_gpus": world, "batch_per_gpu": a.batch, "size": a.size,
-                          "dtype": "f32" if a.fp32 else "bf16", "act_checkpoint": bool(a.checkpoint),
+                          "dtype": "f32" if a.fp32 else "bf16", "act_checkpoint": not a.no_checkpoint,
                           "loss": round(loss.item(), 4), "kernel_ms": cats,
                           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
     if world > 1:
