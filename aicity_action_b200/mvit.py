@@ -9,6 +9,7 @@ the positional-embedding add and the pooled head run in libmvit_b200.so; see att
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 
 import torch
@@ -274,6 +275,11 @@ class MViT(nn.Module):
 
         self.norm_stem = norm_layer(embed_dim) if cfg.MVIT.NORM_STEM else None
         self.act_checkpoint = bool(cfg.MODEL.ACT_CHECKPOINT)
+        # MODEL.ACT_CHECKPOINT trades a second forward for activation memory.  The fused path never stores a score
+        # matrix, so a clip @448 keeps ~1.6 GB of bf16 activations: on a 180 GB B200 the flag is honoured only when the
+        # estimate does not fit the free memory ("auto"); MVIT_B200_ACT_CHECKPOINT=always|never overrides.
+        self.act_checkpoint_policy = os.environ.get("MVIT_B200_ACT_CHECKPOINT", "auto")
+        self._ckpt_decision = {}
 
         self.blocks = nn.ModuleList()
         for i in range(depth):
@@ -351,6 +357,26 @@ class MViT(nn.Module):
             self._b200_pos = slot
         return slot[1]
 
+    def _checkpoint_needed(self, x):
+        """`x`: tokens entering block 0.  Stored activations per token are ~14.5 block-widths of the compute dtype per
+        block (LN inputs, qkv, pooled q/k/v, attention output, MLP hidden) summed over the blocks."""
+        if self.act_checkpoint_policy == "always":
+            return True
+        if self.act_checkpoint_policy == "never":
+            return False
+        key = (tuple(x.shape), x.dtype, x.device)
+        if key not in self._ckpt_decision:
+            tokens, est = x.shape[0] * x.shape[1], 0
+            thw = list(self.patch_dims)
+            for blk in self.blocks:
+                est += tokens * 14.5 * max(blk.dim, blk.dim_out) * x.element_size()
+                new_thw = blk.out_thw(thw)
+                tokens = tokens * (new_thw[0] * new_thw[1] * new_thw[2]) // (thw[0] * thw[1] * thw[2])
+                thw = new_thw
+            free, _ = torch.cuda.mem_get_info(x.device)
+            self._ckpt_decision[key] = est * 1.5 > free      # keep activations when they fit with 50 % headroom
+        return self._ckpt_decision[key]
+
     def forward_features(self, x, dtype):
         T, H, W = self.patch_dims
         stem_params = [self.patch_embed.proj.weight, self.patch_embed.proj.bias]
@@ -378,8 +404,9 @@ class MViT(nn.Module):
         if self.norm_stem is not None:
             x = AG.layernorm(x, self.norm_stem.weight, self.norm_stem.bias, self.norm_stem.eps)
         thw = [T, H, W]
+        use_ckpt = self.act_checkpoint and x.requires_grad and torch.is_grad_enabled() and self._checkpoint_needed(x)
         for blk in self.blocks:
-            if self.act_checkpoint and x.requires_grad and torch.is_grad_enabled():
+            if use_ckpt:
                 # MODEL.ACT_CHECKPOINT (video_model_builder.py:988-1036 wraps every block in fairscale's checkpoint_wrapper)
                 thw_in = list(thw)
                 x = torch.utils.checkpoint.checkpoint(lambda t, b=blk, s=thw_in: b(t, s)[0], x, use_reentrant=False)

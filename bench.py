@@ -330,7 +330,8 @@ def run_ours(args):
         line["train"] = {"value": world * B * train_steps / (ms_train * 1e-3), "unit": "clips/s",
                          "ms_per_step": ms_train / train_steps, "steps": train_steps, "batch_per_gpu": B,
                          "gpu_launches": train_launches,
-                         "what": "forward + backward (MODEL.ACT_CHECKPOINT True, DropPath 0.4, head dropout 0.5) + "
+                         "what": "forward + backward (MODEL.ACT_CHECKPOINT True under the 'auto' policy: activations fit in HBM so "
+                                 "nothing is recomputed; DropPath 0.4, head dropout 0.5) + "
                                  "grad-clip + AdamW, bf16 activations / fp32 master weights"
                                  + (", DDP gradient all-reduce over NCCL" if world > 1 else "")}
     if world == 1 and not args.no_cpu_baseline:

@@ -29,7 +29,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--fp32", action="store_true")
-    ap.add_argument("--no-checkpoint", action="store_true", help="keep activations instead of MODEL.ACT_CHECKPOINT")
+    ap.add_argument("--no-checkpoint", action="store_true", help="MODEL.ACT_CHECKPOINT False")
+    ap.add_argument("--checkpoint-policy", default="auto", choices=["auto", "always", "never"],
+                    help="how MODEL.ACT_CHECKPOINT True is honoured (auto: only when activations do not fit)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -42,6 +44,7 @@ def main():
                             "MODEL.DROPOUT_RATE", 0.5])
     torch.manual_seed(0)
     model = MViT(cfg).cuda().train()
+    model.act_checkpoint_policy = a.checkpoint_policy
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
@@ -83,7 +86,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "train_clips_per_sec", "value": round(a.batch * world / (ms.item() / 1e3), 2),
                           "ms_per_step": round(ms.item(), 2), "n_gpus": world, "batch_per_gpu": a.batch, "size": a.size,
-                          "dtype": "f32" if a.fp32 else "bf16", "act_checkpoint": not a.no_checkpoint,
+                          "dtype": "f32" if a.fp32 else "bf16", "act_checkpoint": not a.no_checkpoint, "checkpoint_policy": a.checkpoint_policy,
                           "loss": round(loss.item(), 4), "kernel_ms": cats,
                           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
     if world > 1:
