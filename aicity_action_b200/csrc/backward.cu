@@ -421,67 +421,84 @@ __global__ void __launch_bounds__(256) pool_conv_dgrad_kernel(const T *__restric
   }
 }
 
-// Vectorised form of the same gather: thread = (input token*head, 16-byte channel group), so the index arithmetic is
-// amortised over 8 (bf16) / 4 (fp32) channels and dy is read with 16-byte loads.  Needs 16-byte aligned rows.
+// Vectorised, divergence-free form of the same gather.  thread = (input token, 16-byte channel group); at any time a CTA
+// only holds tokens of ONE frame t and ONE residue class (h mod sh, w mod sw), so which of the <= 27 taps reach an output
+// is decided per CTA: the contributing taps (1.5 per strided axis on average) are compacted into a short list in shared
+// memory and every thread runs a branch-free loop over it (border taps are masked, not skipped), which lets the dy loads
+// of several taps be in flight together.  blockIdx = (class-and-chunk id of a grid-stride loop, batch*head).
 template <typename T>
 __global__ void __launch_bounds__(256) pool_conv_dgrad_vec_kernel(const T *__restrict__ dy, const float *__restrict__ weight,
-                                                                  T *__restrict__ dx, PoolBwdParams p) {
+                                                                  T *__restrict__ dx, PoolBwdParams p, int nsplit) {
   constexpr int N = Vec16<T>::N;
   extern __shared__ __align__(16) float w_s[];       // [taps][d]
+  __shared__ int4 s_list[27];                        // (weight row offset, output frame, dho, dwo) of the live taps
+  __shared__ int s_n;
   const int taps = p.kt * p.kh * p.kw;
   for (int i = threadIdx.x; i < taps * p.d; i += blockDim.x) {
     const int tap = i / p.d, c = i - tap * p.d;
     w_s[i] = weight[c * taps + tap];
   }
-  __syncthreads();
   const int groups = p.d / N;
-  const int L = p.T * p.H * p.W, Lo = p.To * p.Ho * p.Wo;
-  const int64_t total = (int64_t)p.B * L * p.heads * groups;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int g = (int)(i % groups);
-    const int64_t o = i / groups;
-    const int head = (int)(o % p.heads);
-    const int64_t bl = o / p.heads;
-    const int l = (int)(bl % L), b = (int)(bl / L);
-    const int w = l % p.W, h = (l / p.W) % p.H, t = l / (p.W * p.H);
-    int tv[3], hv[3], wv[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int tn = t + p.pt - a, hn = h + p.ph - a, wn = w + p.pw - a;
-      const int tq = tn / p.st, hq = hn / p.sh, wq = wn / p.sw;
-      tv[a] = (a < p.kt && tn >= 0 && tq * p.st == tn && tq < p.To) ? tq : -1;
-      hv[a] = (a < p.kh && hn >= 0 && hq * p.sh == hn && hq < p.Ho) ? hq : -1;
-      wv[a] = (a < p.kw && wn >= 0 && wq * p.sw == wn && wq < p.Wo) ? wq : -1;
-    }
-    float acc[N];
-#pragma unroll
-    for (int e = 0; e < N; ++e) acc[e] = 0.f;
-    const T *dyb = dy + ((int64_t)(b * p.heads + head) * Lo) * p.d + g * N;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (tv[a] < 0) continue;
-#pragma unroll
-      for (int bq = 0; bq < 3; ++bq) {
-        if (hv[bq] < 0) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (wv[c] < 0) continue;
-          float v[N];
-          Vec16<T>::load(dyb + (int64_t)((tv[a] * p.Ho + hv[bq]) * p.Wo + wv[c]) * p.d, v);
-          const float *pw = w_s + ((a * p.kh + bq) * p.kw + c) * p.d + g * N;
-#pragma unroll
-          for (int e = 0; e < N; e += 4) {
-            const float4 w4 = *reinterpret_cast<const float4 *>(pw + e);
-            acc[e] = fmaf(v[e], w4.x, acc[e]);
-            acc[e + 1] = fmaf(v[e + 1], w4.y, acc[e + 1]);
-            acc[e + 2] = fmaf(v[e + 2], w4.z, acc[e + 2]);
-            acc[e + 3] = fmaf(v[e + 3], w4.w, acc[e + 3]);
+  const int Lo = p.To * p.Ho * p.Wo;
+  const int Hc = (p.H + p.sh - 1) / p.sh, Wc = (p.W + p.sw - 1) / p.sw;
+  const int b = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
+  const T *dy_bh = dy + (int64_t)blockIdx.y * Lo * p.d;
+  T *dx_bh = dx + b * p.x_bs + head * p.x_hs;
+  const int total = Hc * Wc * groups;
+  const int classes = p.sh * p.sw * p.T;
+  for (int work = blockIdx.x; work < classes * nsplit; work += gridDim.x) {
+    const int cls = work / nsplit, split = work - cls * nsplit;
+    const int t = cls % p.T, res = cls / p.T, rh = res / p.sw, rw = res % p.sw;
+    __syncthreads();                                 // previous list no longer in use (and w_s staged, first pass)
+    if (threadIdx.x == 0) {
+      int n = 0;
+      for (int a = 0; a < p.kt; ++a) {
+        const int tn = t + p.pt - a;
+        if (tn < 0 || tn % p.st != 0 || tn / p.st >= p.To) continue;
+        for (int bq = 0; bq < p.kh; ++bq) {
+          const int eh = rh + p.ph - bq;
+          if (eh % p.sh != 0) continue;
+          for (int c = 0; c < p.kw; ++c) {
+            const int ew = rw + p.pw - c;
+            if (ew % p.sw != 0) continue;
+            s_list[n++] = make_int4(((a * p.kh + bq) * p.kw + c) * p.d, tn / p.st, eh / p.sh, ew / p.sw);
           }
         }
       }
+      s_n = n;
     }
-    Vec16<T>::store(dx + b * p.x_bs + (int64_t)l * p.x_ls + head * p.x_hs + g * N, acc);
+    __syncthreads();
+    const int nv = s_n;
+    for (int i = split * blockDim.x + threadIdx.x; i < total; i += nsplit * blockDim.x) {
+      const int r = i / groups, g = i - r * groups;
+      const int hq = r / Wc, wq = r - hq * Wc;
+      const int h = hq * p.sh + rh, w = wq * p.sw + rw;
+      if (h >= p.H || w >= p.W) continue;
+      float acc[N];
+#pragma unroll
+      for (int e = 0; e < N; ++e) acc[e] = 0.f;
+      const T *dyb = dy_bh + g * N;
+#pragma unroll 4
+      for (int n = 0; n < nv; ++n) {
+        const int4 e4 = s_list[n];
+        const int ho = hq + e4.z, wo = wq + e4.w;
+        const bool ok = (unsigned)ho < (unsigned)p.Ho && (unsigned)wo < (unsigned)p.Wo;
+        float v[N];
+        Vec16<T>::load(dyb + (ok ? ((e4.y * p.Ho + ho) * p.Wo + wo) * p.d : 0), v);
+        const float m = ok ? 1.f : 0.f;
+        const float *pw = w_s + e4.x + g * N;
+#pragma unroll
+        for (int e = 0; e < N; e += 4) {
+          const float4 w4 = *reinterpret_cast<const float4 *>(pw + e);
+          acc[e] = fmaf(v[e] * m, w4.x, acc[e]);
+          acc[e + 1] = fmaf(v[e + 1] * m, w4.y, acc[e + 1]);
+          acc[e + 2] = fmaf(v[e + 2] * m, w4.z, acc[e + 2]);
+          acc[e + 3] = fmaf(v[e + 3] * m, w4.w, acc[e + 3]);
+        }
+      }
+      const int l = (t * p.H + h) * p.W + w;
+      Vec16<T>::store(dx_bh + (int64_t)l * p.x_ls + g * N, acc);
+    }
   }
 }
 
@@ -711,14 +728,19 @@ static int pool_bwd_dispatch(int what, const void *x, const void *dy, const floa
   const int Lo = p.To * p.Ho * p.Wo, L = p.T * p.H * p.W;
   const size_t wsm = (size_t)p.kt * p.kh * p.kw * p.d * sizeof(float);
   const int64_t vb = 16 / (int64_t)sizeof(T);
-  const bool vec_ok = what == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 &&
+  const bool vec_ok = what == 0 && (int64_t)p.B * p.heads < 65536 && (int64_t)p.sh * p.sw * p.T < (1 << 20) &&
+                      (int64_t)L * p.d < ((int64_t)1 << 30) &&
+                      ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 &&
                       p.x_bs % vb == 0 && p.x_ls % vb == 0 && p.x_hs % vb == 0 && p.d % vb == 0;
 #define POOL_BWD_CASE(NC)                                                                                             \
   case NC:                                                                                                            \
     if (what == 0 && vec_ok) {                                                                                        \
-      const int64_t items = (int64_t)p.B * L * p.heads * (p.d / Vec16<T>::N);                                         \
-      const int64_t blocks = std::min<int64_t>((items + 255) / 256, (int64_t)num_sms() * 16);                         \
-      pool_conv_dgrad_vec_kernel<T><<<(unsigned)blocks, 256, wsm, st>>>(static_cast<const T *>(dy), weight, static_cast<T *>(dx), p); \
+      const int classes = p.sh * p.sw * p.T, bh = p.B * p.heads;                                                      \
+      const int64_t items = (int64_t)((p.H + p.sh - 1) / p.sh) * ((p.W + p.sw - 1) / p.sw) * (p.d / Vec16<T>::N);     \
+      const int want = (16 * num_sms() + bh - 1) / bh;                 /* CTAs per (batch, head) */                    \
+      const int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>((want + classes - 1) / classes, (items + 511) / 512)); \
+      dim3 grid((unsigned)std::max(1, std::min(classes * nsplit, want)), (unsigned)bh);                               \
+      pool_conv_dgrad_vec_kernel<T><<<grid, 256, wsm, st>>>(static_cast<const T *>(dy), weight, static_cast<T *>(dx), p, nsplit); \
     } else if (what == 0) {                                                                                           \
       const int64_t blocks = std::min<int64_t>(((int64_t)p.B * L * p.heads + 7) / 8, (int64_t)num_sms() * 16);       \
       pool_conv_dgrad_kernel<T, NC><<<(unsigned)blocks, 256, wsm, st>>>(static_cast<const T *>(dy), weight, static_cast<T *>(dx), p); \
