@@ -87,7 +87,7 @@ namespace dq {
 constexpr int BQ = 128, BKV = 64;
 constexpr int kStages = 4;
 constexpr int kStageBytes = 2 * kTile64;            // K | V
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;                       // 4 control warps + 2 streams x 8 dS warps (two per lane quarter)
 constexpr int kSmemBytes = 4 * kTile128 + kStages * kStageBytes + 512 + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColDQ = 256;         // stream i: S at 128 i, dP at 128 i + 64, dQ at 256 + 96 i
@@ -141,7 +141,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&ds_ready[i], 128);
+      mbar_init(&ds_ready[i], 256);
       mbar_init(&dq_done[i], 1);
     }
     fence_barrier_init();
@@ -156,7 +156,6 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {
       // -------------------------------------------------------------- TMA producer
       const int ntile = two ? 2 : 1;
@@ -184,20 +183,20 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         constexpr uint32_t idesc_dq = make_idesc_bf16(BQ, D, 0, 1);    // A = dS (TMEM) x B = K (MN-major)
         const uint32_t sq = smem_u32(sQ) + i * kTile128, sdo = smem_u32(sdO) + i * kTile128, skv = smem_u32(sKV);
         const uint32_t tS = tmem_base + kColS + i * 128, tdP = tS + 64, tdQ = tmem_base + kColDQ + i * D;
+        // descriptors are built once; every MMA only advances the start-address field (one add on the issue path)
+        const uint64_t dsc_q = make_smem_desc(sq, 16, 512, SWZ_64B), dsc_do = make_smem_desc(sdo, 16, 512, SWZ_64B);
+        const uint64_t dsc_k0 = make_smem_desc(skv, 16, 512, SWZ_64B);                 // K-major view of stage 0
+        const uint64_t dsc_kmn0 = make_smem_desc(skv, kChunk64, 512, SWZ_64B);         // MN-major view of stage 0
         auto issue_sdp = [&](int s) {
-          const uint32_t k0 = skv + s * kStageBytes, v0 = k0 + kTile64;
+          const uint64_t dk = desc_advance(dsc_k0, s * kStageBytes), dv = desc_advance(dk, kTile64);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t step = (k & 1) * 32;
-            umma_ss(tS, make_smem_desc(sq + (k >> 1) * kChunk128 + step, 16, 512, SWZ_64B),
-                    make_smem_desc(k0 + (k >> 1) * kChunk64 + step, 16, 512, SWZ_64B), idesc_s, k != 0);
-          }
+          for (int k = 0; k < D / 16; ++k)
+            umma_ss(tS, desc_advance(dsc_q, (k >> 1) * kChunk128 + (k & 1) * 32),
+                    desc_advance(dk, (k >> 1) * kChunk64 + (k & 1) * 32), idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t step = (k & 1) * 32;
-            umma_ss(tdP, make_smem_desc(sdo + (k >> 1) * kChunk128 + step, 16, 512, SWZ_64B),
-                    make_smem_desc(v0 + (k >> 1) * kChunk64 + step, 16, 512, SWZ_64B), idesc_s, k != 0);
-          }
+          for (int k = 0; k < D / 16; ++k)
+            umma_ss(tdP, desc_advance(dsc_do, (k >> 1) * kChunk128 + (k & 1) * 32),
+                    desc_advance(dv, (k >> 1) * kChunk64 + (k & 1) * 32), idesc_s, k != 0);
           umma_commit(&sdp_full[i]);
         };
         mbar_wait(q_full, 0);
@@ -208,11 +207,10 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           const int s = j % kStages;
           mbar_wait(&ds_ready[i], j & 1);              // dS(j) is in TMEM (over S)
           tc_fence_after();
-          const uint32_t k0 = skv + s * kStageBytes;
+          const uint64_t dkmn = desc_advance(dsc_kmn0, s * kStageBytes);
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)           // K tile read MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
-            umma_ts(tdQ, tS + k * 8, make_smem_desc(k0 + k * 16 * 64, kChunk64, 512, SWZ_64B), idesc_dq,
-                    (j > 0 || k != 0));
+            umma_ts(tdQ, tS + k * 8, desc_advance(dkmn, k * 16 * 64), idesc_dq, (j > 0 || k != 0));
           umma_commit(&kv_empty[s]);
           if (j + 1 < nkv) {
             const int s2 = (j + 1) % kStages;
@@ -225,10 +223,10 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    // ---------------------------------------------------------------- dS warps: thread = query row
-    const int i = (warp - 4) >> 2;
-    const int quarter = warp & 3;
+    // ---------------------------------------------------------------- dS warps: thread = query row; the two warps of
+    // a lane quarter split the 64 key columns of a tile (backward needs no cross-column reduction)
+    const int i = (warp - 4) >> 3;
+    const int quarter = warp & 3, colhalf = ((warp - 4) >> 2) & 1;
     if (i == 0 || two) {
       const int row = q0 + i * BQ + quarter * 32 + lane;
       const bool live = row < p.Lq;
@@ -242,43 +240,45 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(&sdp_full[i], j & 1);
         tc_fence_after();
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t s[32], dp[32];
-          tmem_ld32(tS + half * 32, s);
-          tmem_ld32(tdP + half * 32, dp);
+          uint32_t s[16], dp[16];
+          tmem_ld16(tS + colhalf * 32 + half * 16, s);
+          tmem_ld16(tdP + colhalf * 32 + half * 16, dp);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < 8; ++e) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * e]), __uint_as_float(s[2 * e + 1])), c2, nl2);
             const float2 pe = make_float2(ex2_approx(x.x), ex2_approx(x.y));
             const float2 t = __fadd2_rn(make_float2(__uint_as_float(dp[2 * e]), __uint_as_float(dp[2 * e + 1])), nd2);
             const float2 ds = __fmul2_rn(pe, t);
-            pk[half * 16 + e] = pack_bf16x2_alu(ds.x, ds.y);
+            pk[half * 8 + e] = pack_bf16x2_alu(ds.x, ds.y);
           }
         }
-        tmem_st32(tS, pk);                             // dS (bf16) over the first 32 columns of S
+        // dS (bf16) goes over the first 32 columns of S: the partner warp must have read them first
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + i * 4 + quarter) : "memory");
+        tmem_st16(tS + colhalf * 16, pk);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&ds_ready[i]);
       }
-      // ---- epilogue: dQ = scale * acc (+ dO)
+      // ---- epilogue: dQ = scale * acc (+ dO); colhalf 0 stores channels 0..47, colhalf 1 channels 48..95
       mbar_wait(&dq_done[i], 0);
       tc_fence_after();
-      bf16 *dqrow = p.dq + ((int64_t)bh * p.Lq + row) * D;
-      const bf16 *dorow = p.dout + (((int64_t)b * p.Lq + row) * p.heads + head) * D;
+      bf16 *dqrow = p.dq + ((int64_t)bh * p.Lq + row) * D + colhalf * 48;
+      const bf16 *dorow = p.dout + (((int64_t)b * p.Lq + row) * p.heads + head) * D + colhalf * 48;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tdQ + c * 32, o);
+        uint32_t o[16];
+        tmem_ld16(tdQ + colhalf * 48 + c * 16, o);
         tmem_ld_wait();
         if (live) {
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
+          for (int v4 = 0; v4 < 2; ++v4) {
             uint32_t w[4];
             uint4 gv = make_uint4(0, 0, 0, 0);
-            if (p.add_q) gv = *reinterpret_cast<const uint4 *>(dorow + c * 32 + v4 * 8);
+            if (p.add_q) gv = *reinterpret_cast<const uint4 *>(dorow + c * 16 + v4 * 8);
             const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -287,7 +287,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
               w[e] = *reinterpret_cast<uint32_t *>(&h);
             }
-            *reinterpret_cast<uint4 *>(dqrow + c * 32 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(dqrow + c * 16 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
@@ -304,7 +304,7 @@ constexpr int BK = 128, BQ = 64;
 constexpr int kStages = 5;
 constexpr int kStageBytes = 2 * kTile64;            // Q | dO
 constexpr int kVecBytes = 512;                      // lse2[64] | delta[64] fp32
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                       // 4 control warps + 8 P/dS warps (two per TMEM lane quarter)
 constexpr int kSmemBytes = 2 * kTile128 + kStages * (kStageBytes + kVecBytes) + 512 + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColDK = 256, kColDV = 352;      // buffer b: S^T at 128 b, dP^T at 128 b + 64
@@ -358,7 +358,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&pds_ready[i], 128);
+      mbar_init(&pds_ready[i], 256);
     }
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -398,21 +398,21 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     constexpr uint32_t idesc_acc = make_idesc_bf16(BK, D, 0, 1);    // A = P^T / dS^T (TMEM) x B = dO / Q (MN-major)
     const uint32_t sk = smem_u32(sK), sv = smem_u32(sV), sring = smem_u32(sRing);
     const uint32_t tdK = tmem_base + kColDK, tdV = tmem_base + kColDV;
+    // descriptors are built once; every MMA only advances the start-address field (one add on the issue path)
+    const uint64_t dsc_k = make_smem_desc(sk, 16, 512, SWZ_64B), dsc_v = make_smem_desc(sv, 16, 512, SWZ_64B);
+    const uint64_t dsc_r0 = make_smem_desc(sring, 16, 512, SWZ_64B);                   // K-major view of ring stage 0
+    const uint64_t dsc_rmn0 = make_smem_desc(sring, kChunk64, 512, SWZ_64B);           // MN-major view of ring stage 0
     auto issue_sdp = [&](int s, int bf) {
-      const uint32_t qa = sring + s * kStageBytes, da = qa + kTile64;
+      const uint64_t dq = desc_advance(dsc_r0, s * kStageBytes), dd = desc_advance(dq, kTile64);
       const uint32_t tS = tmem_base + bf * 128, tdP = tS + 64;
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) {
-        const uint32_t step = (k & 1) * 32;
-        umma_ss(tS, make_smem_desc(sk + (k >> 1) * kChunk128 + step, 16, 512, SWZ_64B),
-                make_smem_desc(qa + (k >> 1) * kChunk64 + step, 16, 512, SWZ_64B), idesc_s, k != 0);
-      }
+      for (int k = 0; k < D / 16; ++k)
+        umma_ss(tS, desc_advance(dsc_k, (k >> 1) * kChunk128 + (k & 1) * 32),
+                desc_advance(dq, (k >> 1) * kChunk64 + (k & 1) * 32), idesc_s, k != 0);
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) {
-        const uint32_t step = (k & 1) * 32;
-        umma_ss(tdP, make_smem_desc(sv + (k >> 1) * kChunk128 + step, 16, 512, SWZ_64B),
-                make_smem_desc(da + (k >> 1) * kChunk64 + step, 16, 512, SWZ_64B), idesc_s, k != 0);
-      }
+      for (int k = 0; k < D / 16; ++k)
+        umma_ss(tdP, desc_advance(dsc_v, (k >> 1) * kChunk128 + (k & 1) * 32),
+                desc_advance(dd, (k >> 1) * kChunk64 + (k & 1) * 32), idesc_s, k != 0);
       umma_commit(&sdp_full[bf]);
     };
     mbar_wait(kv_full, 0);
@@ -425,14 +425,14 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const int s = j % kStages, bf = j & 1;
       mbar_wait(&pds_ready[bf], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t qa = sring + s * kStageBytes, da = qa + kTile64;
+      const uint64_t dqmn = desc_advance(dsc_rmn0, s * kStageBytes), ddmn = desc_advance(dqmn, kTile64);
       const uint32_t tS = tmem_base + bf * 128, tdP = tS + 64;
 #pragma unroll
       for (int k = 0; k < BQ / 16; ++k)
-        umma_ts(tdV, tS + k * 8, make_smem_desc(da + k * 16 * 64, kChunk64, 512, SWZ_64B), idesc_acc, (j > 0 || k != 0));
+        umma_ts(tdV, tS + k * 8, desc_advance(ddmn, k * 16 * 64), idesc_acc, (j > 0 || k != 0));
 #pragma unroll
       for (int k = 0; k < BQ / 16; ++k)
-        umma_ts(tdK, tdP + k * 8, make_smem_desc(qa + k * 16 * 64, kChunk64, 512, SWZ_64B), idesc_acc, (j > 0 || k != 0));
+        umma_ts(tdK, tdP + k * 8, desc_advance(dqmn, k * 16 * 64), idesc_acc, (j > 0 || k != 0));
       umma_commit(&qd_empty[s]);
       if (j + 2 < n) {
         const int s2 = (j + 2) % kStages;
@@ -443,8 +443,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     umma_commit(acc_done);
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- P^T / dS^T warps: thread = key
-    const int quarter = warp & 3;
+    // ---------------------------------------------------------------- P^T / dS^T warps: thread = key, and the two
+    // warps of a lane quarter split the 64 query columns of a tile (no cross-column reduction is needed in backward)
+    const int quarter = warp & 3, colhalf = (warp - 4) >> 2;
     const int key = key0 + quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
@@ -454,18 +455,17 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       mbar_wait(&sdp_full[bf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + lane_base + bf * 128, tdP = tS + 64;
-      const float4 *vl = reinterpret_cast<const float4 *>(sVec + s * kVecBytes);
+      const float4 *vl = reinterpret_cast<const float4 *>(sVec + s * kVecBytes) + colhalf * 8;
       const float4 *vd = vl + 16;
-      uint32_t pkp[32], pkd[32];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      uint32_t pkp[16], pkd[16];
+      {
         uint32_t sc[32], dp[32];
-        tmem_ld32(tS + half * 32, sc);
-        tmem_ld32(tdP + half * 32, dp);
+        tmem_ld32(tS + colhalf * 32, sc);
+        tmem_ld32(tdP + colhalf * 32, dp);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 l4 = vl[half * 8 + g], d4 = vd[half * 8 + g];
+          const float4 l4 = vl[g], d4 = vd[g];
           const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -476,39 +476,37 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const float2 t = __fadd2_rn(make_float2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])),
                                         make_float2(-dv[h2 * 2], -dv[h2 * 2 + 1]));
             const float2 ds = __fmul2_rn(pe, t);
-            pkp[half * 16 + g * 2 + h2] = pack_bf16x2_alu(pe.x, pe.y);
-            pkd[half * 16 + g * 2 + h2] = pack_bf16x2_alu(ds.x, ds.y);
+            pkp[g * 2 + h2] = pack_bf16x2_alu(pe.x, pe.y);
+            pkd[g * 2 + h2] = pack_bf16x2_alu(ds.x, ds.y);
           }
         }
       }
-      tmem_st32(tS, pkp);                              // P^T (bf16) over S^T, dS^T over dP^T
-      tmem_st32(tdP, pkd);
+      // P^T / dS^T (bf16) go over the first 32 columns of S^T / dP^T: the partner warp must have read them first
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      tmem_st16(tS + colhalf * 16, pkp);
+      tmem_st16(tdP + colhalf * 16, pkd);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&pds_ready[bf]);
     }
-    // ---- epilogue: fp32 vector reductions into dK (scaled) and dV
+    // ---- epilogue: fp32 vector reductions; colhalf 0 -> dK (scaled), colhalf 1 -> dV
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const bool live = key < p.Lk;
-    float *dkrow = p.dk + ((int64_t)bh * p.Lk + key) * D, *dvrow = p.dv + ((int64_t)bh * p.Lk + key) * D;
+    const uint32_t tA = tmem_base + lane_base + (colhalf == 0 ? kColDK : kColDV);
+    float *dst = (colhalf == 0 ? p.dk : p.dv) + ((int64_t)bh * p.Lk + key) * D;
+    const float mul = colhalf == 0 ? p.scale : 1.0f;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t tA = tmem_base + lane_base + (which == 0 ? kColDK : kColDV);
-      float *dst = which == 0 ? dkrow : dvrow;
-      const float mul = which == 0 ? p.scale : 1.0f;
+    for (int c = 0; c < 3; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tA + c * 32, o);
+      tmem_ld_wait();
+      if (live) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tA + c * 32, o);
-        tmem_ld_wait();
-        if (live) {
-#pragma unroll
-          for (int v4 = 0; v4 < 8; ++v4) {
-            const float4 val = make_float4(__uint_as_float(o[v4 * 4]) * mul, __uint_as_float(o[v4 * 4 + 1]) * mul,
-                                           __uint_as_float(o[v4 * 4 + 2]) * mul, __uint_as_float(o[v4 * 4 + 3]) * mul);
-            atomicAdd(reinterpret_cast<float4 *>(dst + c * 32 + v4 * 4), val);
-          }
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const float4 val = make_float4(__uint_as_float(o[v4 * 4]) * mul, __uint_as_float(o[v4 * 4 + 1]) * mul,
+                                         __uint_as_float(o[v4 * 4 + 2]) * mul, __uint_as_float(o[v4 * 4 + 3]) * mul);
+          atomicAdd(reinterpret_cast<float4 *>(dst + c * 32 + v4 * 4), val);
         }
       }
     }

@@ -173,24 +173,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DO, 0, 1);    // A = P (TMEM),    B = [V | 1] (MN-major)
         const uint32_t sq = smem_u32(sQ) + i * kQTileBytes, skv = smem_u32(sKV);
         const uint32_t tS_i = tmem_base + kColS + i * 128, tO_i = tmem_base + kColO + i * DO;
+        // descriptors are built once; every MMA only advances the start-address field (one add on the issue path)
+        const uint64_t dsc_q = make_smem_desc(sq, 16, 512, SWZ_64B);
+        const uint64_t dsc_k0 = make_smem_desc(skv, 16, 512, SWZ_64B);                        // K of stage 0, K-major
+        const uint64_t dsc_v0 = make_smem_desc(skv + kKTileBytes, kKChunkBytes, 512, SWZ_64B);   // V of stage 0, MN-major
         auto issue_qk = [&](int s, int b) {
-          const uint32_t k0 = skv + s * kStageBytes;
+          const uint64_t dk = desc_advance(dsc_k0, s * kStageBytes);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t step = (k & 1) * 32;
-            umma_ss(tS_i + b * BKV, make_smem_desc(sq + (k >> 1) * kQChunkBytes + step, 16, 512, SWZ_64B),
-                    make_smem_desc(k0 + (k >> 1) * kKChunkBytes + step, 16, 512, SWZ_64B), idesc_qk, k != 0);
-          }
+          for (int k = 0; k < D / 16; ++k)
+            umma_ss(tS_i + b * BKV, desc_advance(dsc_q, (k >> 1) * kQChunkBytes + (k & 1) * 32),
+                    desc_advance(dk, (k >> 1) * kKChunkBytes + (k & 1) * 32), idesc_qk, k != 0);
           umma_commit(&s_full[i * 2 + b]);
         };
         auto issue_pv = [&](int s, int b, bool accumulate) {
-          const uint32_t v0 = skv + s * kStageBytes + kKTileBytes;
+          const uint64_t dv = desc_advance(dsc_v0, s * kStageBytes);
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            // V tile: [64 kv rows][32-col chunk] x3; MN-major: LBO = chunk stride, SBO = 8 rows x 64 B
-            umma_ts(tO_i, tS_i + b * BKV + k * 8, make_smem_desc(v0 + k * 16 * 64, kKChunkBytes, 512, SWZ_64B),
-                    idesc_pv, (accumulate || k != 0));
-          }
+          for (int k = 0; k < BKV / 16; ++k)   // V tile: [64 kv rows][32-col chunk] x3 (+ ones); LBO = chunk stride, SBO = 512
+            umma_ts(tO_i, tS_i + b * BKV + k * 8, desc_advance(dv, k * 16 * 64), idesc_pv, (accumulate || k != 0));
           umma_commit(&o_done[i]);
         };
         mbar_wait(q_full, 0);

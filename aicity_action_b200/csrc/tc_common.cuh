@@ -276,6 +276,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (swizzle << 61);
 }
+// Advance a descriptor's start address by `bytes` (a multiple of 16): one add on the low word instead of rebuilding
+// the descriptor.  Valid while the address field does not overflow its 14 bits, i.e. for any shared-memory address.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, dense:
 //   [4,6) D format 1 = f32 | [7,10) A format 1 = bf16 | [10,13) B format 1 = bf16
 //   [15] A major (0 = K) | [16] B major (0 = K, 1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
