@@ -190,6 +190,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
+      // descriptors of stage 0, built once; each MMA only advances the start-address field
+      const uint64_t dsc_a = make_smem_desc(smem_u32(sA), 16, 1024, SWZ_128B);
+      const uint64_t dsc_b = make_smem_desc(smem_u32(sB), 16, 1024, SWZ_128B);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -201,11 +204,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + stage * C::kABytes), b0 = smem_u32(sB + stage * C::kBBytes);
+          const uint64_t da0 = desc_advance(dsc_a, stage * C::kABytes), db0 = desc_advance(dsc_b, stage * C::kBBytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(a0 + k * UMMA_K * 2, 16, 1024, SWZ_128B);
-            const uint64_t db = make_smem_desc(b0 + k * UMMA_K * 2, 16, 1024, SWZ_128B);
+            const uint64_t da = desc_advance(da0, k * UMMA_K * 2), db = desc_advance(db0, k * UMMA_K * 2);
             if constexpr (PAIR) umma_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
             else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
           }

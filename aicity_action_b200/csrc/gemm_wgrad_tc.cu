@@ -94,16 +94,15 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
   } else if (warp == 1 && lane == 0) {
     // A and B both MN-major; 16 more columns (the ones box) when this CTA also reduces the bias gradient
     const uint32_t idesc = with_bias ? make_idesc_bf16(BP, BQ + 16, 1, 1) : make_idesc_bf16(BP, BQ, 1, 1);
-    const uint32_t base = smem_u32(smem);
+    const uint64_t dsc0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024, SWZ_128B);   // stage 0, advanced per MMA
     for (int i = 0; i < chunks; ++i) {
       const int s = i % C::kStages;
       mbar_wait(&full[s], (i / C::kStages) & 1);
       tc_fence_after();
-      const uint32_t a = base + s * C::kStageBytes, b = a + C::kABoxes * kBoxBytes;
+      const uint64_t da = desc_advance(dsc0, s * C::kStageBytes), db = desc_advance(da, C::kABoxes * kBoxBytes);
 #pragma unroll
       for (int k = 0; k < BMT / 16; ++k)   // 16 tokens = 16 rows x 128 B; LBO = next 64-feature box, SBO = 8 rows x 128 B
-        umma_ss(tmem_base, make_smem_desc(a + k * 16 * 128, kBoxBytes, 1024, SWZ_128B),
-                make_smem_desc(b + k * 16 * 128, kBoxBytes, 1024, SWZ_128B), idesc, (i > 0 || k != 0));
+        umma_ss(tmem_base, desc_advance(da, k * 16 * 128), desc_advance(db, k * 16 * 128), idesc, (i > 0 || k != 0));
       umma_commit(&empty[s]);
     }
     umma_commit(done);
