@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmvit_b200.so")
 
 F32, BF16 = 0, 1
 POOL_CONV, POOL_MAX, POOL_AVG = 0, 1, 2
-EPI_NONE, EPI_GELU = 0, 1
+EPI_NONE, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float

@@ -77,9 +77,10 @@ class _Linear(Function):
         if row_scale is not None:                       # DropPath: a per-sample constant multiplier
             nb = row_scale.numel()
             dz = (dy.view(nb, -1) * row_scale.to(dy.dtype).view(nb, 1)).view(dy.shape)
-        if ctx.gelu:                                    # rebuild the pre-activation instead of having stored it
-            pre = ops.linear(x, cached_weight(weight, x.dtype), bias)
-            dz = ops.gelu_bwd(pre, dz)
+        if ctx.gelu:
+            # the pre-activation is rebuilt (not stored in forward) and differentiated in the same GEMM's epilogue:
+            # dz <- dz * gelu'(x.W^T + b), with dz riding in as the epilogue's "residual" tile
+            dz = ops.linear(x, cached_weight(weight, x.dtype), bias, residual=dz, gelu_grad=True)
         dx = ops.linear(dz, cached_weight_t(weight, x.dtype)) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):

@@ -167,11 +167,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_pairs_kernel(const T *__res
 
 // ------------------------------------------------------------------------------------------------ GELU backward
 // dpre = dy * d/dx[ x * Phi(x) ] = dy * (Phi(x) + x * phi(x)),  exact erf form (common.py:20 nn.GELU)
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
 template <typename T>
 __global__ void gelu_bwd_kernel(const T *__restrict__ pre, const T *__restrict__ dy, T *__restrict__ dpre, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

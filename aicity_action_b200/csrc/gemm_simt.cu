@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearArgs a) {
       float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
       if (a.epilogue == MVIT_EPI_GELU) v = gelu_erf(v);
       if (a.row_scale) v *= rs;
-      if (res) v += to_f32(res[(a.res_period ? m % a.res_period : m) * a.ldr + n]);
+      if (a.epilogue == MVIT_EPI_GELU_GRAD) v = gelu_grad(v) * to_f32(res[m * a.ldr + n]);
+      else if (res) v += to_f32(res[(a.res_period ? m % a.res_period : m) * a.ldr + n]);
       y[m * a.ldy + n] = from_f32<T>(v);
     }
   }
@@ -81,7 +82,10 @@ extern "C" int mvit_linear_fwd(const void *x, const void *w, const float *bias, 
   using namespace mvit;
   MVIT_REQUIRE(x && w && y, "linear: null pointer");
   MVIT_REQUIRE(M >= 0 && N > 0 && K > 0, "linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
-  MVIT_REQUIRE(epilogue == MVIT_EPI_NONE || epilogue == MVIT_EPI_GELU, "linear: unknown epilogue %d", epilogue);
+  MVIT_REQUIRE(epilogue == MVIT_EPI_NONE || epilogue == MVIT_EPI_GELU || epilogue == MVIT_EPI_GELU_GRAD,
+               "linear: unknown epilogue %d", epilogue);
+  MVIT_REQUIRE(epilogue != MVIT_EPI_GELU_GRAD || (residual && residual_row_period == 0 && !row_scale),
+               "linear: EPI_GELU_GRAD needs a full residual (the upstream gradient) and no row_scale");
   MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "linear: unknown dtype %d", dtype);
   MVIT_REQUIRE(ldy >= N && (!residual || ldr >= N), "linear: leading dimension smaller than N");
   MVIT_REQUIRE(!row_scale || rows_per_sample > 0, "linear: row_scale needs rows_per_sample");

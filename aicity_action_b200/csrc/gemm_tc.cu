@@ -93,6 +93,27 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   return __ffma2_rn(x, phi, __fmul2_rn(x, make_float2(0.5f, 0.5f)));
 }
 
+// d/dx GELU(x) = Phi(x) + x*phi(x): Phi from the same polynomial, phi(x) = exp(-x^2/2)/sqrt(2 pi) with one MUFU.EX2.
+__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
+  const float2 xc = make_float2(fminf(fmaxf(x.x, -4.f), 4.f), fminf(fmaxf(x.y, -4.f), 4.f));
+  const float2 v = __fmul2_rn(xc, xc);
+  float2 r = make_float2(-1.5806889130942636e-09f, -1.5806889130942636e-09f);
+  r = __ffma2_rn(r, v, make_float2(1.2170519880783104e-07f, 1.2170519880783104e-07f));
+  r = __ffma2_rn(r, v, make_float2(-4.100723799638217e-06f, -4.100723799638217e-06f));
+  r = __ffma2_rn(r, v, make_float2(8.066566078923643e-05f, 8.066566078923643e-05f));
+  r = __ffma2_rn(r, v, make_float2(-0.0010481934295967221f, -0.0010481934295967221f));
+  r = __ffma2_rn(r, v, make_float2(0.009664841927587986f, 0.009664841927587986f));
+  r = __ffma2_rn(r, v, make_float2(-0.06617535650730133f, -0.06617535650730133f));
+  r = __ffma2_rn(r, v, make_float2(0.3988475501537323f, 0.3988475501537323f));
+  const float2 cdf = __ffma2_rn(r, xc, make_float2(0.5f, 0.5f));
+  const float2 u = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  float ex, ey;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(u.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(u.y));
+  const float2 xpdf = __fmul2_rn(x, make_float2(0.39894228040143267794f * ex, 0.39894228040143267794f * ey));
+  return __fadd2_rn(cdf, xpdf);
+}
+
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -305,6 +326,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (p.epilogue == MVIT_EPI_GELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = gelu_fast2(x[j]);
+          } else if (p.epilogue == MVIT_EPI_GELU_GRAD) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = gelu_grad_fast2(x[j]);
           }
           if (p.row_scale) {
 #pragma unroll
@@ -315,10 +339,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (p.has_residual) {
             const uint4 rv = *slot;
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            if (p.epilogue == MVIT_EPI_GELU_GRAD) {       // the "residual" is the upstream gradient: multiply
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[j].x += __uint_as_float(rw[j] << 16);
-              x[j].y += __uint_as_float(rw[j] & 0xffff0000u);
+              for (int j = 0; j < 4; ++j) {
+                x[j].x *= __uint_as_float(rw[j] << 16);
+                x[j].y *= __uint_as_float(rw[j] & 0xffff0000u);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                x[j].x += __uint_as_float(rw[j] << 16);
+                x[j].y += __uint_as_float(rw[j] & 0xffff0000u);
+              }
             }
           }
           uint32_t o[4];

@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (BF16, EPI_GELU, EPI_NONE, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, POOL_AVG,
+from ._lib import (BF16, EPI_GELU, EPI_GELU_GRAD, EPI_NONE, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, POOL_AVG,
                    POOL_CONV, POOL_MAX, check)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -99,9 +99,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
            residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
            gelu: bool = False, out: Optional[torch.Tensor] = None, impl: int = IMPL_AUTO,
-           residual_row_period: int = 0) -> torch.Tensor:
+           residual_row_period: int = 0, gelu_grad: bool = False) -> torch.Tensor:
     """y = epi(x·wᵀ + bias)·row_scale + residual ; x [..., K], w [N, K] (same dtype as x).
-    residual_row_period = P > 0: `residual` is a [P, N] table and row m adds row m % P."""
+    residual_row_period = P > 0: `residual` is a [P, N] table and row m adds row m % P.
+    gelu_grad: backward helper, y = residual · gelu'(x·wᵀ + bias) (`residual` = the upstream gradient)."""
     global launch_count
     _need_cuda(x, w, bias, residual, row_scale)
     x = x.contiguous()
@@ -123,7 +124,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     with _Timed("linear", 2.0 * M * N * K):
         check(_lib.load().mvit_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(row_scale),
                                           rows_per_sample, _ptr(y), M, N, K, N, N, int(residual_row_period),
-                                          EPI_GELU if gelu else EPI_NONE, _dt(x), impl, _stream()),
+                                          EPI_GELU_GRAD if gelu_grad else (EPI_GELU if gelu else EPI_NONE), _dt(x), impl,
+                                          _stream()),
               "mvit_linear_fwd")
     launch_count += 1
     return y

@@ -41,6 +41,7 @@ extern "C" {
 /* epilogues of mvit_linear_fwd */
 #define MVIT_EPI_NONE 0
 #define MVIT_EPI_GELU 1 /* exact erf GELU (common.py:20 nn.GELU) */
+#define MVIT_EPI_GELU_GRAD 2 /* backward helper: y = residual * gelu'(x.w^T + bias)  (residual = upstream gradient) */
 
 /* implementation selector of the GEMM / attention entry points */
 #define MVIT_IMPL_AUTO 0    /* bf16 -> tcgen05, f32 -> fp32 FMA kernels */

@@ -363,3 +363,17 @@ def test_fp16_autocast_is_served_by_the_bf16_kernels():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             b = m([x])
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+def test_gelu_bwd_kernel_and_fused_epilogue(dtype):
+    """Standalone gelu' kernel and the GEMM epilogue form (y = dy * gelu'(x.W^T + b)) against autograd of F.gelu."""
+    M, K, N = 300, 96, 384
+    x, w, b, dy = (synth_tensor(8, n, s) for n, s in (("x", (M, K)), ("w", (N, K)), ("b", (N,)), ("dy", (M, N))))
+    w = w * K ** -0.5
+    pre = leaf((x.to(dtype).float() @ w.to(dtype).float().t() + b))
+    F.gelu(pre).backward(dy.to(dtype).float())
+    got = ops.gelu_bwd(pre.detach().to(dtype).cuda(), dy.to(dtype).cuda())
+    check("gelu_bwd", got, pre.grad, TOL[dtype])
+    fused = ops.linear(x.to(dtype).cuda(), w.to(dtype).cuda(), b.cuda(), residual=dy.to(dtype).cuda(), gelu_grad=True)
+    check("gelu_grad epilogue", fused, pre.grad, TOL[dtype])
