@@ -130,3 +130,33 @@ def test_sliding_window_runner_matches_direct_inference():
             fr = video.get_batch(SW.frame_indices(*wins[w], cfg.DATA.NUM_FRAMES, 200)).unsqueeze(0).cuda()
             direct = m([ops.preprocess_u8(fr, torch.bfloat16)])[0].cpu().numpy()
             assert abs(direct - preds[w][2]).max() < 2e-3
+
+
+def test_forward_is_cuda_graph_capturable():
+    """The eval forward (side-stream pooling included) captures into a CUDA graph and replays bit-identically: the C ABI
+    never synchronises or allocates, TMA descriptors are kernel parameters encoded per launch."""
+    c = MODEL_CASES[0]
+    cfg = aicity_cfg(c["yaml"], tiny_cfg_overrides(c))
+    m = MViT(cfg).eval()
+    load_synth(m, c["seed"])
+    m = m.cuda()
+    x = synth_clip(c["seed"], 2, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda().bfloat16()
+    static_x = x.clone()
+    with torch.no_grad():
+        eager = m([static_x]).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                m([static_x])
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            static_out = m([static_x])
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_out, eager)
+        static_x.copy_(x.flip(0))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_out, eager.flip(0))
