@@ -91,11 +91,14 @@ class SlidingWindowRunner:
 
     def __init__(self, model: Callable, num_frames: int = 16, sampling_rate: int = 4, proposal_stride: int = 16,
                  batch_size: int = 8, dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
-                 rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None):
+                 rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None,
+                 use_cuda_graph: bool = False):
         self.model, self.T, self.rate = model, num_frames, sampling_rate
         self.length, self.stride = num_frames * sampling_rate, proposal_stride   # run_action...py:76
         self.batch_size, self.dtype, self.device = batch_size, dtype, device
         self.rank, self.world, self.group = rank, world, group
+        self.use_cuda_graph = use_cuda_graph and device is not None
+        self._graphed = None
         if preprocess is None and device is not None:
             from . import ops
             preprocess = lambda u8: ops.preprocess_u8(u8, dtype)
@@ -115,6 +118,14 @@ class SlidingWindowRunner:
             frames = torch.stack([video.get_batch(frame_indices(*windows[w], self.T, len(video))) for w in ids])
             if self.device is not None:
                 frames = frames.pin_memory().to(self.device, non_blocking=True)
+            if self.use_cuda_graph and len(ids) == self.batch_size:
+                # full batches replay one captured graph (uint8 frames in, normalisation fused into the patch embed);
+                # the ragged last batch takes the eager path
+                if self._graphed is None:
+                    from .graphed import GraphedForward
+                    self._graphed = GraphedForward(self.model, frames.clone())
+                outs.append(self._graphed(frames).float().cpu())
+                continue
             clip = self.preprocess(frames) if self.preprocess is not None else frames
             outs.append(self.model([clip]).float().cpu())
         scores = torch.cat(outs) if outs else torch.zeros((0, 0))

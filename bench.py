@@ -191,9 +191,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from aicity_action_b200.graphed import GraphedForward
+    use_graph = not args.no_cuda_graph
     with torch.no_grad():
         for _ in range(W):
             out = model([dev_clip])
+        # the public GraphedForward wrapper: the forward (171 launches) is captured once per input buffer and replayed
+        # with one host call, so the step rate does not depend on how many ranks share the host's cores
+        fwd = GraphedForward(model, dev_clip) if use_graph else (lambda: model([dev_clip]))
+        for _ in range(2):
+            out = fwd()
         barrier()
         # ---- timed region 1: device-resident inputs ----------------------------------------
         sampler = ClockSampler(local)
@@ -203,7 +210,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(K):
-            out = model([dev_clip])
+            out = fwd()
         e1.record()
         barrier()
         launches = (ops.launch_count - n0)
@@ -225,6 +232,13 @@ def run_ours(args):
         # ---- timed region 2: end to end from pinned host memory ----------------------------
         copy_stream = torch.cuda.Stream()
         dbuf = [torch.empty_like(host[0], device=dev) for _ in range(2)]
+        for b_ in dbuf:
+            b_.copy_(host[0])
+        if use_graph:
+            g0 = GraphedForward(model, dbuf[0])
+            fwd_u8 = [g0, GraphedForward(model, dbuf[1], pool=g0.pool)]
+        else:
+            fwd_u8 = [lambda b_=b_: model([b_]) for b_ in dbuf]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
 
@@ -243,7 +257,7 @@ def run_ours(args):
                 if i + 1 < n:
                     upload(i + 1)
                 cur.wait_event(ready[i % 2])
-                probs = model([dbuf[i % 2]])         # uint8 frames: normalise + fold + patch-embed on the device
+                probs = fwd_u8[i % 2]()              # uint8 frames: normalise + fold + patch-embed on the device
                 freed[i % 2].record(cur)
                 probs_host.copy_(probs, non_blocking=True)
             cur.synchronize()
@@ -317,7 +331,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"{CONFIG_NAME} eval forward, batch {B} per GPU, random init",
                    "l2": "inputs (154 MB bf16 clip batch) and activations exceed the 126 MB L2",
-                   "parallelism": f"replicated model, {world} independent clip batches"},
+                   "parallelism": f"replicated model, {world} independent clip batches",
+                   "launch": "CUDA graph replay (aicity_action_b200.graphed.GraphedForward)" if use_graph else "eager"},
         "model_tflops": value * FLOP_PER_CLIP / 1e12 / world,
         "frac_of_bf16_peak_whole_model": value * FLOP_PER_CLIP / 1e12 / world / peaks["bf16_tflops_sustained"],
         "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "clips/s",
@@ -353,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="issue every launch from Python instead of graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
