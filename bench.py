@@ -324,6 +324,15 @@ def run_ours(args):
                 "frac": attn.get("frac"), "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
                 "share_of_step": attn.get("ms_per_step", 0.0) / (ms_instr / K) if ms_instr else None,
                 "instrumented_ms_per_step": ms_instr / K}
+    # DRAM bytes per attention launch from the committed ncu pass of this same command (profiles/README.md); algorithmic
+    # bytes per launch (q, k, v read + out written once) printed beside it
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
+            tr = json.load(f)
+        roofline["traffic"] = tr["avg_dram_bytes_per_launch"]
+        roofline["traffic_source"] = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     value = world * B * K / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,
