@@ -136,7 +136,7 @@ class _PoolQKV(Function):
         B, N, C3 = qkv.shape
         d = C3 // (3 * heads)
         qkv5 = qkv.view(B, N, 3, heads, d)
-        outs, shapes = [], []
+        outs, shapes, pres = [], [], [None, None, None]
         for i in range(3):
             t = qkv5[:, :, i].permute(0, 2, 1, 3)
             w, g, b = params[3 * i:3 * i + 3]
@@ -145,18 +145,23 @@ class _PoolQKV(Function):
                 shapes.append(list(thw))
             else:
                 kernel, stride, eps = descs[i]
-                ln = (g, b, eps) if g is not None else None
-                o, s = ops.attention_pool_heads(t, list(thw), kernel, stride, mode="conv", weight=w, ln=ln)
+                if g is not None and ops.pool_save_supported(t, kernel, stride):
+                    # keep the conv output for the LayerNorm backward (one extra store) instead of recomputing it
+                    o, pres[i], s = ops.attention_pool_heads_save(t, list(thw), kernel, stride, w, (g, b, eps))
+                else:
+                    ln = (g, b, eps) if g is not None else None
+                    o, s = ops.attention_pool_heads(t, list(thw), kernel, stride, mode="conv", weight=w, ln=ln)
                 shapes.append(s)
             outs.append(o)
-        ctx.save_for_backward(qkv, *params)
+        ctx.save_for_backward(qkv, *params, *pres)
         ctx.meta = (heads, list(thw), descs)
         ctx.out_tokens = [s[0] * s[1] * s[2] for s in shapes]
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
-        qkv, *params = ctx.saved_tensors
+        qkv, *rest = ctx.saved_tensors
+        params, pres = rest[:9], rest[9:]
         heads, thw, descs = ctx.meta
         B, N, C3 = qkv.shape
         d = C3 // (3 * heads)
@@ -178,8 +183,11 @@ class _PoolQKV(Function):
             kernel, stride, eps = descs[i]
             x_view = qkv5[:, :, i]
             dg = db = None
-            if g is not None:                           # rebuild the conv output, differentiate the LayerNorm
-                conv, _ = ops.attention_pool_heads(x_view.permute(0, 2, 1, 3), thw, kernel, stride, mode="conv", weight=w)
+            if g is not None:                           # differentiate the LayerNorm on the saved (or rebuilt) conv output
+                conv = pres[i]
+                if conv is None:
+                    conv, _ = ops.attention_pool_heads(x_view.permute(0, 2, 1, 3), thw, kernel, stride, mode="conv",
+                                                       weight=w)
                 dy, dg, db = ops.layernorm_bwd(conv, g, dy, eps)
             dw = torch.zeros((d, kernel[0] * kernel[1] * kernel[2]), dtype=torch.float32, device=qkv.device)
             ops.attention_pool_bwd(1, x_view, strides, dy, None, None, dw, B, heads, d, thw, kernel, stride)

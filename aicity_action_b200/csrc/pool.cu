@@ -187,12 +187,10 @@ static int maxpool_tokens_try(const void *in, void *out, const PoolParams &p, in
 
 }  // namespace mvit
 
-extern "C" int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
-                                       const float *weight, const float *gamma, const float *beta,
-                                       void *out, int64_t out_bs, int64_t out_ls, int64_t out_hs, int B,
-                                       int heads, int d, int T, int H, int W, int kt, int kh, int kw,
-                                       int st, int sh, int sw, int mode, int has_cls, float eps,
-                                       int dtype, void *stream) {
+static int pool_fwd_impl(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs, const float *weight,
+                         const float *gamma, const float *beta, void *out, int64_t out_bs, int64_t out_ls, int64_t out_hs,
+                         void *pre_ln_out, int B, int heads, int d, int T, int H, int W, int kt, int kh, int kw, int st,
+                         int sh, int sw, int mode, int has_cls, float eps, int dtype, void *stream) {
   using namespace mvit;
   MVIT_REQUIRE(in && out, "attention_pool: null pointer");
   MVIT_REQUIRE(B >= 0 && heads > 0 && d > 0 && T > 0 && H > 0 && W > 0, "attention_pool: bad shape");
@@ -217,11 +215,34 @@ extern "C" int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in
   p.has_cls = has_cls ? 1 : 0;
   p.has_ln = gamma ? 1 : 0;
   p.eps = eps;
+  p.pre_out = pre_ln_out;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int r = pool_tiled_try(in, weight, gamma, beta, out, p, mode, dtype, s);
   if (r <= 0) return r;
+  MVIT_REQUIRE(pre_ln_out == nullptr, "attention_pool: the pre-LayerNorm output is only produced by the tuned kernel "
+                                      "(3x3x3 depthwise conv, head_dim 96, stride (1,s,s), s in {1,2,4,8}, 16-byte aligned)");
   r = maxpool_tokens_try(in, out, p, mode, dtype, s);
   if (r <= 0) return r;
   if (dtype == MVIT_F32) return dispatch_generic<float>(in, weight, gamma, beta, out, p, mode, s);
   return dispatch_generic<bf16>(in, weight, gamma, beta, out, p, mode, s);
+}
+
+extern "C" int mvit_attention_pool_fwd(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
+                                       const float *weight, const float *gamma, const float *beta,
+                                       void *out, int64_t out_bs, int64_t out_ls, int64_t out_hs, int B,
+                                       int heads, int d, int T, int H, int W, int kt, int kh, int kw,
+                                       int st, int sh, int sw, int mode, int has_cls, float eps,
+                                       int dtype, void *stream) {
+  return pool_fwd_impl(in, in_bs, in_ls, in_hs, weight, gamma, beta, out, out_bs, out_ls, out_hs, nullptr, B, heads, d, T, H,
+                       W, kt, kh, kw, st, sh, sw, mode, has_cls, eps, dtype, stream);
+}
+
+extern "C" int mvit_attention_pool_fwd_save(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
+                                            const float *weight, const float *gamma, const float *beta, void *out,
+                                            int64_t out_bs, int64_t out_ls, int64_t out_hs, void *pre_ln_out, int B,
+                                            int heads, int d, int T, int H, int W, int kt, int kh, int kw, int st,
+                                            int sh, int sw, float eps, int dtype, void *stream) {
+  MVIT_REQUIRE(pre_ln_out && gamma && beta, "attention_pool_fwd_save: needs the LayerNorm and the second output");
+  return pool_fwd_impl(in, in_bs, in_ls, in_hs, weight, gamma, beta, out, out_bs, out_ls, out_hs, pre_ln_out, B, heads, d, T,
+                       H, W, kt, kh, kw, st, sh, sw, MVIT_POOL_CONV, 0, eps, dtype, stream);
 }

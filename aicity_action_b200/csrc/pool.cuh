@@ -8,6 +8,8 @@ struct PoolParams {
   int B, heads, d, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo;
   int has_cls, has_ln;
   float eps;
+  void *pre_out = nullptr;   // optional second output of the tuned kernel: the pooled values BEFORE the LayerNorm,
+                             // contiguous [B, heads, L', d] (saved for backward instead of recomputing the conv)
 };
 
 // tuned path (pool_tiled.cu); returns 1 if it does not apply, 0 on launch, <0 on error

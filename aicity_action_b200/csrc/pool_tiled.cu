@@ -163,6 +163,23 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
           const float4 v = *reinterpret_cast<const float4 *>(stg + jc * kStgPitch + part * CH + 4 * k);
           x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
         }
+        const int ho = ho0 + hl, wo = wo0 + cl0 + jc;
+        const bool inside = ho < p.Ho && wo < p.Wo;
+        if (p.pre_out != nullptr && inside) {      // training: keep the conv output for the LayerNorm backward
+          T *prow = static_cast<T *>(p.pre_out) +
+                    (((int64_t)blockIdx.y * p.To + to) * p.Ho * p.Wo + (int64_t)ho * p.Wo + wo) * 96 + part * CH;
+          if constexpr (sizeof(T) == 2) {
+#pragma unroll
+            for (int k = 0; k < CH / 4; ++k) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(x[4 * k], x[4 * k + 1]), h1 = __floats2bfloat162_rn(x[4 * k + 2], x[4 * k + 3]);
+              *reinterpret_cast<uint2 *>(prow + 4 * k) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < CH / 4; ++k)
+              *reinterpret_cast<float4 *>(prow + 4 * k) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+          }
+        }
         if (p.has_ln) {
           float sum = 0.f;
 #pragma unroll
@@ -186,8 +203,7 @@ pool_tiled_kernel(const T *__restrict__ in, const float *__restrict__ weight, co
             x[4 * k + 3] = fmaf(x[4 * k + 3] * rstd, g.w, bt.w);
           }
         }
-        const int ho = ho0 + hl, wo = wo0 + cl0 + jc;
-        if (ho < p.Ho && wo < p.Wo) {
+        if (inside) {
           T *row = out + (int64_t)b * p.out_bs + (int64_t)((to * p.Ho + ho) * p.Wo + wo) * p.out_ls +
                    (int64_t)head * p.out_hs + part * CH;
           if constexpr (sizeof(T) == 2) {

@@ -172,6 +172,34 @@ def attention_pool_heads(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[i
     return out, out_thw
 
 
+def pool_save_supported(x: torch.Tensor, kernel: Sequence[int], stride: Sequence[int]) -> bool:
+    """Whether mvit_attention_pool_fwd_save applies to this q/k/v view (the tuned kernel's conditions)."""
+    es = x.element_size()
+    return (list(kernel) == [3, 3, 3] and x.shape[3] == 96 and stride[0] == 1 and stride[1] == stride[2]
+            and stride[1] in (1, 2, 4, 8) and x.data_ptr() % 16 == 0
+            and all((x.stride(i) * es) % 16 == 0 for i in range(3)))
+
+
+def attention_pool_heads_save(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[int], stride: Sequence[int],
+                              weight: torch.Tensor, ln: Tuple[torch.Tensor, torch.Tensor, float]):
+    """Training forward of conv pooling + LayerNorm: -> (pooled [B, heads, L', d], pre-LayerNorm values, thw')."""
+    global launch_count
+    _need_cuda(x, weight, ln[0], ln[1])
+    B, heads, L, d = x.shape
+    out_thw = pooled_thw(thw, kernel, stride)
+    Lo = out_thw[0] * out_thw[1] * out_thw[2]
+    out = torch.empty((B, heads, Lo, d), dtype=x.dtype, device=x.device)
+    pre = torch.empty_like(out)
+    w = _f32c(weight).reshape(d, -1)
+    with _Timed("pool_conv", float(B * heads * d * L + 2 * out.numel()) * x.element_size()):
+        check(_lib.load().mvit_attention_pool_fwd_save(
+            _ptr(x), x.stride(0), x.stride(2), x.stride(1), _ptr(w), _ptr(_f32c(ln[0])), _ptr(_f32c(ln[1])), _ptr(out),
+            heads * Lo * d, d, Lo * d, _ptr(pre), B, heads, d, thw[0], thw[1], thw[2], *kernel, *stride, float(ln[2]),
+            _dt(x), _stream()), "mvit_attention_pool_fwd_save")
+    launch_count += 1
+    return out, pre, out_thw
+
+
 def attention_pool_tokens(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[int], stride: Sequence[int], *,
                           mode: str = "max", has_cls: bool = False, d: int = 96):
     """x: [B, L, C] channels-last tokens -> [B, L', C] (skip-path pooling, attention.py:427-432)."""

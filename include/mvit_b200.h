@@ -167,6 +167,17 @@ int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, c
                         int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N,
                         void *stream);
 
+/* Training form of mvit_attention_pool_fwd (conv mode + LayerNorm, no cls token): additionally writes the pooled values
+ * BEFORE the LayerNorm to pre_ln_out (contiguous [B, heads, L', d], dtype), which the LayerNorm backward needs — saving
+ * them costs one extra store, recomputing them costs the whole convolution.  Only the tuned kernel produces it
+ * (3x3x3 depthwise conv, head_dim 96, stride (1,s,s) with s in {1,2,4,8}, 16-byte aligned strides); otherwise an error
+ * is returned and the caller recomputes with mvit_attention_pool_fwd(gamma = NULL). */
+int mvit_attention_pool_fwd_save(const void *in, int64_t in_bs, int64_t in_ls, int64_t in_hs,
+                                 const float *weight, const float *gamma, const float *beta, void *out,
+                                 int64_t out_bs, int64_t out_ls, int64_t out_hs, void *pre_ln_out, int B, int heads,
+                                 int d, int T, int H, int W, int kt, int kh, int kw, int st, int sh, int sw,
+                                 float eps, int dtype, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward entry points (the reference has no explicit backward code: tools/train_net.py:229-246 calls
  * loss.backward() and autograd differentiates attention.py / common.py op by op; these are those
