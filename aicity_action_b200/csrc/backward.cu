@@ -600,7 +600,10 @@ extern "C" int mvit_layernorm_bwd(const void *x, const float *gamma, const void 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 7) == 0;
   if (channels % 2 == 0 && channels <= 768 && aligned) {
-    const unsigned blocks = (unsigned)std::min<int64_t>((rows + 15) / 16, (int64_t)num_sms() * 8);
+    // one wave of resident CTAs (register-limited: 1 / 2 / 4 per SM for C <= 768 / 384 / 192), at least 64 rows each, so
+    // the per-CTA dgamma/dbeta reduction (2C atomics) is paid a few hundred times, not once per 16 rows
+    const int per_sm = channels > 384 ? 1 : (channels > 192 ? 2 : 4);
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, (int64_t)num_sms() * per_sm));
     const size_t smem3 = 3 * (size_t)channels * sizeof(float);
 #define LN_BWD_PAIRS(T, NP, LPR)                                                                                       \
   layernorm_bwd_pairs_kernel<T, NP, LPR><<<blocks, 256, smem3, st>>>(static_cast<const T *>(x), gamma,                 \
