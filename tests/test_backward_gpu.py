@@ -377,3 +377,28 @@ def test_gelu_bwd_kernel_and_fused_epilogue(dtype):
     check("gelu_bwd", got, pre.grad, TOL[dtype])
     fused = ops.linear(x.to(dtype).cuda(), w.to(dtype).cuda(), b.cuda(), residual=dy.to(dtype).cuda(), gelu_grad=True)
     check("gelu_grad epilogue", fused, pre.grad, TOL[dtype])
+
+
+def test_full_size_backward_kernels_cross_check():
+    """BASELINE-size shapes (MViTv2-B @448, stage 3, one clip): the tcgen05 backward kernels against the independent
+    CUDA-core kernels on the same bf16 data (both accumulate in fp32), where the CPU oracle would take minutes."""
+    torch.manual_seed(0)
+    B, h, Lq, Lk, d = 1, 4, 6272, 1568, 96
+    q, k, v = (torch.randn(B, h, L, d, device="cuda").bfloat16() for L in (Lq, Lk, Lk))
+    do = torch.randn(B, Lq, h * d, device="cuda").bfloat16()
+    out, lse = ops.attention(q, k, v, d ** -0.5, True, want_lse=True)
+    tc = ops.attention_bwd(q, k, v, out, do, lse, d ** -0.5, True)
+    simt = ops.attention_bwd(q, k, v, out, do, lse, d ** -0.5, True, impl=ops.IMPL_SIMT)
+    for name, a, b in zip(("dq", "dk", "dv"), tc, simt):
+        check(name, a, b, 2e-2)
+    # a size-independent identity: rows of P sum to one, so dV = P^T dO conserves mass: sum_j dv_j = sum_i dO_i
+    dv_sum = tc[2].float().sum(2)                                   # [B, h, d]
+    do_sum = do.float().view(B, Lq, h, d).sum(1)                    # [B, h, d]
+    check("sum(dv) == sum(dO)", dv_sum, do_sum, 2e-2)
+    M, N, K = 50176, 1536, 384
+    dy, x = torch.randn(M, N, device="cuda").bfloat16(), torch.randn(M, K, device="cuda").bfloat16()
+    dw_tc, db_tc = ops.linear_wgrad(dy, x, True)
+    dw_simt, db_simt = ops.linear_wgrad(dy, x, True, impl=ops.IMPL_SIMT)
+    check("dw", dw_tc, dw_simt, 1e-3)
+    check("db", db_tc, db_simt, 1e-3)
+    check("db == column sums", db_tc, dy.float().sum(0), 1e-3)
