@@ -94,3 +94,32 @@ def test_module_attribute_parity():
     assert a.pool_q.weight.shape == (96, 1, 3, 3, 3) and a.norm_q.eps == 1e-5 and abs(a.scale - 96 ** -0.5) < 1e-12
     nopool = MultiScaleAttention(96, num_heads=1, kernel_q=(1, 1, 1), stride_q=(1, 1, 1))
     assert nopool.pool_q is None and nopool.norm_q is None
+
+
+def test_install_into_reference_checkout():
+    """aicity_action_b200.patch.install(): the reference's own build_model(cfg) then returns the drop-in MViT with a
+    state_dict that loads into / from the reference model.  Needs /root/reference (absent on the GPU box -> skipped)."""
+    if not os.path.isdir("/root/reference/slowfast"):
+        pytest.skip("reference checkout not present")
+    import ref_shims
+    ref_shims.install()
+    cfg = ref_shims.ref_cfg("MVITV2_FULL_B_16x4_CONV.yaml", tiny_cfg_overrides(MODEL_CASES[0]))
+    ref_model = ref_shims.ref_build_model(cfg, seed=0)
+    import aicity_action_b200.patch as b200
+    from aicity_action_b200.mvit import MViT
+    import slowfast.models.attention as ref_attn
+    import slowfast.models.build as ref_build
+    saved = (ref_build.MODEL_REGISTRY._obj_map["MViT"], ref_attn.attention_pool, ref_attn.MultiScaleAttention,
+             ref_attn.MultiScaleBlock)
+    try:
+        assert b200.install() == {"registry": True, "attention": True}
+        ours = ref_shims.ref_build_model(cfg, seed=0)
+        assert isinstance(ours, MViT)
+        a, b = ref_model.state_dict(), ours.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        ours.load_state_dict(a, strict=True)
+    finally:
+        ref_build.MODEL_REGISTRY._obj_map["MViT"] = saved[0]
+        ref_attn.attention_pool, ref_attn.MultiScaleAttention, ref_attn.MultiScaleBlock = saved[1:]
