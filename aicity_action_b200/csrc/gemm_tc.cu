@@ -25,8 +25,7 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;                     // 64 bf16 = one 128-byte swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 384
+constexpr int kEpiWarp0 = 4;                             // warps 0-3: TMA, MMA, TMEM alloc, residual producer
 constexpr int kBoxCols = 32;               // output / residual boxes: 128 rows x 32 cols (64 B), SWIZZLE_64B
 constexpr int kBoxBytes = BM * kBoxCols * 2;
 
@@ -47,8 +46,16 @@ template <int BN, bool PAIR> struct Cfg {
   static constexpr int kBoxes = BN / kBoxCols;
   static constexpr int kOutBytes = kBoxes * kBoxBytes;
   static constexpr int kTmemCols = BN == 192 ? 512 : 256;  // 2 accumulators of BN columns, power of two
-  static constexpr int kChunk = BN == 96 ? 16 : 32;        // columns per tcgen05.ld of one epilogue thread
-  static constexpr int kNumChunks = (BN / 2) / kChunk;     // 3 / 2 / 3
+  // Epilogue warps: kParts per TMEM lane quarter, each owning BN / kParts columns of the tile.  The 1-CTA configurations
+  // serve the memory-bound (small-K) layers, where the epilogue IS the kernel: with two warps per scheduler it issued
+  // on 39 % of the cycles (ncu), so they get 3 / 4 parts; the CTA-pair configuration keeps 2 (96 columns a thread).
+  static constexpr int kParts = PAIR ? 2 : (BN == 96 ? 3 : 4);
+  static constexpr int kEpiWarps = 4 * kParts;
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  static constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 384 (pair) / 512 (BN 96) / 640 (BN 128)
+  static constexpr int kCols = BN / kParts;                // columns of one epilogue thread: 96 / 32 / 32
+  static constexpr int kChunk = 32;                        // columns per tcgen05.ld
+  static constexpr int kNumChunks = kCols / kChunk;        // 3 / 1 / 1
   static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
 };
 
@@ -115,7 +122,7 @@ __device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
 }
 
 template <int BN, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<BN, PAIR>::kThreads), 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, Params p) {
   using C = Cfg<BN, PAIR>;
@@ -153,7 +160,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);   // PAIR: both CTAs' epilogues release the leader
+      mbar_init(&tempty[i], PAIR ? 2 * C::kEpiWarps : C::kEpiWarps);   // PAIR: both CTAs' epilogues release the leader
     }
     for (int i = 0; i < C::kNB; ++i) {
       mbar_init(&res_full[i], 1);
@@ -271,11 +278,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------ epilogue: 8 warps
+    // ------------------------------------------------------------ epilogue: kParts warps per TMEM lane quarter
     const int e = warp - kEpiWarp0;
     const int q = e & 3;                               // TMEM lane quarter (== warp % 4)
-    const int hf = e >> 2;                             // which half of the BN columns
-    const int et = threadIdx.x - kEpiWarp0 * 32;       // 0..255
+    const int hf = e >> 2;                             // which part of the BN columns
+    const int et = threadIdx.x - kEpiWarp0 * 32;       // 0..kEpiThreads-1
     const int row = q * 32 + lane;                     // row inside the tile == TMEM lane
     const uint32_t swz = (uint32_t)((row >> 1) & 3);
     int acc = 0, buf = 0;
@@ -298,12 +305,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
       float rs = 1.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + row, p.M - 1) / p.rows_per_sample];
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // this tile's bias slice is visible; previous store was issued
+      asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");   // this tile's bias slice is visible; previous store was issued
       mbar_wait(&res_full[buf], buf_phase);            // buffer is ours (and holds the residual tile, if any)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       uint8_t *obuf = sOut + buf * C::kOutBytes;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hf * (BN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hf * C::kCols;
       uint32_t r[C::kNumChunks][C::kChunk];
 #pragma unroll
       for (int c = 0; c < C::kNumChunks; ++c) {
@@ -313,7 +320,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < C::kNumChunks; ++c) {
-        const int col0 = hf * (BN / 2) + c * C::kChunk;          // first tile column of this chunk
+        const int col0 = hf * C::kCols + c * C::kChunk;          // first tile column of this chunk
 #pragma unroll
         for (int v = 0; v < C::kChunk / 8; ++v) {
           const int col = col0 + v * 8;
@@ -373,7 +380,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       // tile is complete in shared memory -> one thread TMA-stores it
       fence_proxy_async_smem();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(C::kEpiThreads) : "memory");
       if (et == 0) {
         if (p.conv.enabled) {
           const TileCoord tc = conv_tile(p.conv, t / n_tiles);
@@ -495,7 +502,7 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   } else {
     cfg.gridDim = dim3((unsigned)std::min<int64_t>(tiles, num_sms()));
   }
-  cfg.blockDim = dim3(gemm::kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   MVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm::linear_tc_kernel<BN, PAIR>, tx, tw, ty, tr, p));
@@ -546,7 +553,7 @@ int patch_conv_tc(const void *folded, const void *wf, const float *bias, const v
                  {1, Tf, Hf, Wf, Cf / gemm::BK, nt, nh, nw, lo_t, lo_h, lo_w}};
   const int64_t tiles = (M / gemm::BM) * ((N + 95) / 96);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
-  gemm::linear_tc_kernel<96, false><<<grid, gemm::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+  gemm::linear_tc_kernel<96, false><<<grid, C::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
   MVIT_LAUNCH_OK("patch_conv(tcgen05)");
   return 0;
 }
