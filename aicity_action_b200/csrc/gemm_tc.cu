@@ -48,14 +48,14 @@ template <int BN, bool PAIR> struct Cfg {
   static constexpr int kTmemCols = BN == 192 ? 512 : 256;  // 2 accumulators of BN columns, power of two
   // Epilogue warps: kParts per TMEM lane quarter, each owning BN / kParts columns of the tile.  The 1-CTA configurations
   // serve the memory-bound (small-K) layers, where the epilogue IS the kernel: with two warps per scheduler it issued
-  // on 39 % of the cycles (ncu), so they get 3 / 4 parts; the CTA-pair configuration keeps 2 (96 columns a thread).
-  static constexpr int kParts = PAIR ? 2 : (BN == 96 ? 3 : 4);
+  // on 39 % of the cycles (ncu); every configuration now runs 3 (BN 96) or 4 warps per quarter.
+  static constexpr int kParts = BN == 96 ? 3 : 4;
   static constexpr int kEpiWarps = 4 * kParts;
   static constexpr int kEpiThreads = kEpiWarps * 32;
   static constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 384 (pair) / 512 (BN 96) / 640 (BN 128)
-  static constexpr int kCols = BN / kParts;                // columns of one epilogue thread: 96 / 32 / 32
-  static constexpr int kChunk = 32;                        // columns per tcgen05.ld
-  static constexpr int kNumChunks = kCols / kChunk;        // 3 / 1 / 1
+  static constexpr int kCols = BN / kParts;                // columns of one epilogue thread: 48 (BN 192) / 32
+  static constexpr int kChunk = kCols % 32 == 0 ? 32 : 16; // columns per tcgen05.ld
+  static constexpr int kNumChunks = kCols / kChunk;        // 3 / 1
   static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
 };
 
