@@ -56,22 +56,32 @@ class SyntheticVideo:
     (seed, f) only, so any rank can materialise any frame without I/O.  Frames are uint8 [S, S, 3] RGB — what the
     reference holds after `cv2.resize(frame, (S, S))` (scripts/utils.py:207-211)."""
 
+    PERIOD = 61      # distinct frames per video: frame f is texture f % PERIOD (enough that every window is unique)
+
     def __init__(self, seed: int, num_frames: int, size: int, fps: float = 30.0):
         self.seed, self.num_frames, self.size, self.fps = seed, num_frames, size, fps
         g = torch.Generator().manual_seed(seed)
         self._base = torch.randint(0, 256, (size, size, 3), dtype=torch.uint8, generator=g)
         self._ramp = torch.arange(size, dtype=torch.int32).view(size, 1, 1)
+        self._pool = None
 
     def __len__(self):
         return self.num_frames
 
+    def _texture(self, k: int) -> torch.Tensor:
+        # cheap, deterministic: circular shift of a base texture plus a ramp
+        img = torch.roll(self._base, shifts=(k % self.size, (3 * k) % self.size), dims=(0, 1)).to(torch.int32)
+        return ((img + (self._ramp * (k % 7))) % 256).to(torch.uint8)
+
     def frame(self, f: int) -> torch.Tensor:
-        # cheap, frame-dependent, deterministic: circular shift of a base texture plus a moving ramp
-        img = torch.roll(self._base, shifts=(f % self.size, (3 * f) % self.size), dims=(0, 1)).to(torch.int32)
-        return ((img + (self._ramp * (f % 7))) % 256).to(torch.uint8)
+        return self._texture(int(f) % self.PERIOD)
 
     def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
-        return torch.stack([self.frame(int(i)) for i in idxs])      # [T, S, S, 3]
+        """[T, S, S, 3] uint8: one gather from the (lazily built) texture pool, so that host-side frame synthesis does not
+        bound the benchmark the way a Python loop over frames did."""
+        if self._pool is None:
+            self._pool = torch.stack([self._texture(k) for k in range(self.PERIOD)])
+        return self._pool[torch.as_tensor([int(i) % self.PERIOD for i in idxs])]
 
 
 # ----------------------------------------------------------------------------- the runner
@@ -98,10 +108,14 @@ class SlidingWindowRunner:
         self.batch_size, self.dtype, self.device = batch_size, dtype, device
         self.rank, self.world, self.group = rank, world, group
         self.use_cuda_graph = use_cuda_graph and device is not None
-        self._graphed = None
-        if preprocess is None and device is not None:
+        self._graphed = [None, None]
+        self._dbuf = [None, None]
+        self._copy_stream = None
+        if preprocess is None and device is not None and dtype != torch.bfloat16:
             from . import ops
             preprocess = lambda u8: ops.preprocess_u8(u8, dtype)
+        # bf16 (the default): the model takes the uint8 frames as they are and normalises inside its patch-embed fold, in
+        # the eager and in the graph-replay path alike, so both give identical bits
         self.preprocess = preprocess
 
     def windows_for(self, video) -> List[Tuple[int, int]]:
@@ -110,25 +124,81 @@ class SlidingWindowRunner:
 
     @torch.no_grad()
     def local_scores(self, video, windows: List[Tuple[int, int]]) -> Tuple[List[int], torch.Tensor]:
-        """Scores of this rank's windows: (window ids, [n_local, classes] float32 on CPU)."""
+        """Scores of this rank's windows: (window ids, [n_local, classes] float32 on CPU).
+
+        On a device the batches are pipelined: a host thread gathers and pins the uint8 frames of batch i+1 while batch i
+        runs, uploads go through a copy stream into one of two device buffers, and the per-batch probabilities stay on
+        the device until the video is done (one synchronisation per video instead of one per batch)."""
         mine = shard_windows(len(windows), self.rank, self.world)
-        outs = []
-        for b0 in range(0, len(mine), self.batch_size):
-            ids = mine[b0:b0 + self.batch_size]
-            frames = torch.stack([video.get_batch(frame_indices(*windows[w], self.T, len(video))) for w in ids])
-            if self.device is not None:
-                frames = frames.pin_memory().to(self.device, non_blocking=True)
-            if self.use_cuda_graph and len(ids) == self.batch_size:
-                # full batches replay one captured graph (uint8 frames in, normalisation fused into the patch embed);
-                # the ragged last batch takes the eager path
-                if self._graphed is None:
+        chunks = [mine[b0:b0 + self.batch_size] for b0 in range(0, len(mine), self.batch_size)]
+
+        def host_batch(ids):
+            return torch.stack([video.get_batch(frame_indices(*windows[w], self.T, len(video))) for w in ids])
+
+        if self.device is None:                          # host-only logic (CPU tests with a stub model)
+            outs = []
+            for ids in chunks:
+                frames = host_batch(ids)
+                clip = self.preprocess(frames) if self.preprocess is not None else frames
+                outs.append(self.model([clip]).float().cpu())
+            return mine, (torch.cat(outs) if outs else torch.zeros((0, 0)))
+
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=2)
+
+        def producer():
+            for ids in chunks:
+                q.put(host_batch(ids).pin_memory())
+            q.put(None)
+
+        threading.Thread(target=producer, daemon=True).start()
+        cur = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy = self._copy_stream
+        # the two upload buffers live as long as the runner: the captured graphs read them by address, and a buffer
+        # allocated mid-stream could be a block that kernels already in flight on the compute stream are still using
+        if chunks and len(chunks[0]) == self.batch_size:
+            shape = (self.batch_size, self.T) + tuple(video.get_batch([0]).shape[1:])
+            if self._dbuf[0] is None or tuple(self._dbuf[0].shape) != shape:
+                cur.synchronize()
+                self._dbuf = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._graphed = [None, None]
+        dbuf = self._dbuf
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in freed:
+            ev.record(cur)
+        outs, i = [], 0
+        while True:
+            frames = q.get()
+            if frames is None:
+                break
+            full = frames.shape[0] == self.batch_size
+            slot = i % 2
+            with torch.cuda.stream(copy):
+                copy.wait_event(freed[slot])
+                dev_frames = dbuf[slot] if full else torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
+                dev_frames.copy_(frames, non_blocking=True)
+                ready[slot].record(copy)
+            cur.wait_event(ready[slot])
+            if self.use_cuda_graph and full:
+                # full batches replay a captured graph per upload buffer (uint8 frames in, normalisation fused into the
+                # patch embed); the ragged last batch takes the eager path
+                if self._graphed[slot] is None:
                     from .graphed import GraphedForward
-                    self._graphed = GraphedForward(self.model, frames.clone())
-                outs.append(self._graphed(frames).float().cpu())
-                continue
-            clip = self.preprocess(frames) if self.preprocess is not None else frames
-            outs.append(self.model([clip]).float().cpu())
-        scores = torch.cat(outs) if outs else torch.zeros((0, 0))
+                    pool = next((g.pool for g in self._graphed if g is not None), None)
+                    self._graphed[slot] = GraphedForward(self.model, dbuf[slot], pool=pool)
+                probs = self._graphed[slot]().clone()
+            else:
+                clip = self.preprocess(dev_frames) if self.preprocess is not None else dev_frames
+                probs = self.model([clip])
+                dev_frames.record_stream(cur)
+            freed[slot].record(cur)
+            outs.append(probs.float())
+            i += 1
+        scores = torch.cat(outs).cpu() if outs else torch.zeros((0, 0))
         return mine, scores
 
     def gather(self, n_windows: int, mine: List[int], scores: torch.Tensor, num_classes: int) -> Optional[torch.Tensor]:

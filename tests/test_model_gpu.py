@@ -171,9 +171,18 @@ def test_sliding_window_runner_cuda_graph_matches_eager():
     m = m.cuda()
     video = SW.SyntheticVideo(seed=5, num_frames=300, size=cfg.DATA.TRAIN_CROP_SIZE)
     kw = dict(num_frames=cfg.DATA.NUM_FRAMES, sampling_rate=4, proposal_stride=16, batch_size=4, device=torch.device("cuda"))
-    eager = SW.SlidingWindowRunner(m, **kw).run_video(video, cfg.MODEL.NUM_CLASSES)
-    graphed = SW.SlidingWindowRunner(m, use_cuda_graph=True, **kw).run_video(video, cfg.MODEL.NUM_CLASSES)
-    assert len(eager) == len(graphed) and len(eager) % 4 != 0          # exercises the ragged last batch too
-    for (a0, a1, pa), (b0, b1, pb) in zip(eager, graphed):
-        assert (a0, a1) == (b0, b1)
-        assert abs(pa - pb).max() < 1e-6
+    video2 = SW.SyntheticVideo(seed=6, num_frames=260, size=cfg.DATA.TRAIN_CROP_SIZE)
+    r_eager, r_graph = SW.SlidingWindowRunner(m, **kw), SW.SlidingWindowRunner(m, use_cuda_graph=True, **kw)
+    for vid in (video, video2, video):                # the same runner across videos: upload buffers and graphs are reused
+        eager = r_eager.run_video(vid, cfg.MODEL.NUM_CLASSES)
+        graphed = r_graph.run_video(vid, cfg.MODEL.NUM_CLASSES)
+        assert len(eager) == len(graphed) and len(eager) % 4 != 0          # exercises the ragged last batch too
+        for (a0, a1, pa), (b0, b1, pb) in zip(eager, graphed):
+            assert (a0, a1) == (b0, b1)
+            assert (pa == pb).all()
+    # and against the un-pipelined definition: every window pushed through the model on its own
+    with torch.no_grad():
+        wins = SW.window_list(300, cfg.DATA.NUM_FRAMES * 4, 16)
+        for w in (0, 3, 9, len(wins) - 1):
+            fr = video.get_batch(SW.frame_indices(*wins[w], cfg.DATA.NUM_FRAMES, 300)).unsqueeze(0).cuda()
+            assert abs(m([fr])[0].float().cpu().numpy() - eager[w][2]).max() < 2e-3

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--size", type=int, default=448)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -39,7 +40,8 @@ def main():
     cfg = aicity_cfg("MVITV2_FULL_B_16x4_CONV_448" if a.size == 448 else "MVITV2_FULL_B_16x4_CONV")
     torch.manual_seed(0)
     model = MViT(cfg).eval().to(dev)
-    runner = SW.SlidingWindowRunner(model, batch_size=a.batch, device=dev, rank=rank, world=world)
+    runner = SW.SlidingWindowRunner(model, batch_size=a.batch, device=dev, rank=rank, world=world,
+                                    use_cuda_graph=not a.no_cuda_graph)
     videos = [SW.SyntheticVideo(seed=100 + v, num_frames=a.frames, size=a.size) for v in range(a.views)]
     runner.run_video(SW.SyntheticVideo(seed=1, num_frames=16 * a.batch * world, size=a.size), cfg.MODEL.NUM_CLASSES)  # warm-up
     if world > 1:
@@ -58,6 +60,10 @@ def main():
     if a.check and rank == 0:
         solo = SW.SlidingWindowRunner(model, batch_size=a.batch, device=dev).run_video(videos[0], cfg.MODEL.NUM_CLASSES)
         ok = all(x[0] == y[0] and x[1] == y[1] and (x[2] == y[2]).all() for x, y in zip(solo, results[0]))
+        if not ok:
+            bad = [i for i, (x, y) in enumerate(zip(solo, results[0])) if not (x[2] == y[2]).all()]
+            worst = max(float(abs(x[2] - y[2]).max()) for x, y in zip(solo, results[0]))
+            print(f"check: {len(bad)} of {len(solo)} windows differ (first {bad[:8]}), max |diff| {worst:.3e}", file=sys.stderr)
     if rank == 0:
         print(json.dumps({"metric": "sliding-window windows/s (synthetic 3-view videos, host frame synthesis included)",
                           "value": n_win / float(dt.item()), "unit": "windows/s", "n_gpus": world, "windows": n_win,
