@@ -34,6 +34,7 @@ def main():
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))   # torchrun pins OMP to 1 thread; frame gathering is host work
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
