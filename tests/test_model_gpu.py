@@ -186,3 +186,21 @@ def test_sliding_window_runner_cuda_graph_matches_eager():
         for w in (0, 3, 9, len(wins) - 1):
             fr = video.get_batch(SW.frame_indices(*wins[w], cfg.DATA.NUM_FRAMES, 300)).unsqueeze(0).cuda()
             assert abs(m([fr])[0].float().cpu().numpy() - eager[w][2]).max() < 2e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_cls_token_variants_vs_oracle(dtype):
+    """Secondary variants: a cls token (bypasses pooling, joins LayerNorm and attention), avg / max pooling
+    modes, non-separable pos-embed — run on the generic CUDA kernels, checked against the oracle directly."""
+    for mode, cls, sep in (("conv", True, True), ("max", True, False), ("avg", False, True)):
+        c = MODEL_CASES[0]
+        ovr = tiny_cfg_overrides(c) + ["MVIT.CLS_EMBED_ON", cls, "MVIT.MODE", mode, "MVIT.SEP_POS_EMBED", sep]
+        cfg = aicity_cfg(c["yaml"], ovr)
+        m = MViT(cfg).eval()
+        sd = load_synth(m, c["seed"])
+        m = m.cuda()
+        x = synth_clip(c["seed"], 2, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE)
+        with torch.no_grad():
+            ref = O.mvit_forward(x, sd, O.derive_spec(cfg))
+            got = m([x.cuda().to(dtype)])
+        assert rel_inf(got, ref) < TOL[dtype], (mode, cls, sep)
