@@ -204,3 +204,18 @@ def test_cls_token_variants_vs_oracle(dtype):
             ref = O.mvit_forward(x, sd, O.derive_spec(cfg))
             got = m([x.cuda().to(dtype)])
         assert rel_inf(got, ref) < TOL[dtype], (mode, cls, sep)
+
+
+def test_depth24_32x3_preset_vs_oracle():
+    """The 32-frame depth-24 Aicity preset (16 temporal tokens), full depth at a reduced crop, bf16 vs the oracle."""
+    cfg = aicity_cfg("MVITV2_FULL_B_32x3_CONV.yaml", ["DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64])
+    assert cfg.MVIT.DEPTH == 24 and cfg.DATA.NUM_FRAMES == 32
+    m = MViT(cfg).eval()
+    sd = load_synth(m, 5)
+    m = m.cuda()
+    x = synth_clip(5, 1, cfg.DATA.NUM_FRAMES, 64)
+    with torch.no_grad():
+        ref = O.mvit_forward(x, sd, O.derive_spec(cfg))
+        got = m([x.cuda().bfloat16()])
+    assert rel_inf(got, ref) < 2e-2
+    assert torch.equal(got.argmax(1).cpu(), ref.argmax(1))
