@@ -87,11 +87,12 @@ def attention_pool(tensor, pool, thw_shape, has_cls_embed=True, norm=None, pool2
     mode, k, s, w = desc
     if AG.recording(tensor, w, getattr(norm, "weight", None)):
         # differentiable form: the block's skip-path max pool; q/k/v pooling trains through MultiScaleAttention
-        if tensor.ndim == 3 and mode == "max" and norm is None and not has_cls_embed:
-            return AG.maxpool_tokens(tensor, list(thw_shape), k, s)
-        raise NotImplementedError(
-            "attention_pool: this variant has no backward kernel yet (trainable: MultiScaleAttention's conv pooling "
-            "without cls token, and the [B, L, C] max-pool skip path)")
+        if tensor.ndim == 3 and mode == "max" and norm is None:
+            return AG.maxpool_tokens(tensor, list(thw_shape), k, s, has_cls=has_cls_embed)
+        if tensor.ndim == 4:
+            ln = (norm.weight, norm.bias, norm.eps) if norm is not None else None
+            return AG.pool_heads_generic(tensor, thw_shape, k, s, mode, w, ln, has_cls_embed)
+        raise NotImplementedError("attention_pool: [B, L, C] input is differentiable for max pooling without norm only")
     ln = None
     if norm is not None:
         ln = (norm.weight, norm.bias, norm.eps)
@@ -185,7 +186,7 @@ class MultiScaleAttention(nn.Module):
                 continue
             mode, k, s, w = _pool_desc(pool)
             if mode != "conv" or self.has_cls_embed:
-                raise NotImplementedError("training is implemented for MVIT.MODE == 'conv' without a cls token")
+                return None, None                      # secondary variants: generic differentiable path
             descs.append((tuple(k), tuple(s), norm.eps if norm is not None else None))
             params += [w, getattr(norm, "weight", None), getattr(norm, "bias", None)]
         return tuple(descs), params
@@ -200,8 +201,24 @@ class MultiScaleAttention(nn.Module):
                        for p in m.parameters()]
         if AG.recording(qkv, *pool_params):
             descs, params = self._train_descs()
-            (q, k, v), shapes = AG.pool_qkv(qkv, h, thw_shape, descs, params)
-            return AG.attention(q, k, v, self.scale, self.use_query_residual_pool), shapes[0]
+            if descs is not None:
+                (q, k, v), shapes = AG.pool_qkv(qkv, h, thw_shape, descs, params)
+                return AG.attention(q, k, v, self.scale, self.use_query_residual_pool), shapes[0]
+            # MVIT.MODE avg / max or a cls token: the same dataflow from generic differentiable pieces
+            qkv5g = qkv.view(B, N, 3, h, C // h)
+            parts, out_shape = [], list(thw_shape)
+            for which, (pool, norm) in enumerate(((self.pool_q, getattr(self, "norm_q", None)),
+                                                  (self.pool_k, getattr(self, "norm_k", None)),
+                                                  (self.pool_v, getattr(self, "norm_v", None)))):
+                t = qkv5g[:, :, which].permute(0, 2, 1, 3)
+                if pool is None:
+                    parts.append(t.contiguous())
+                    continue
+                t, shp = attention_pool(t, pool, thw_shape, has_cls_embed=self.has_cls_embed, norm=norm)
+                if which == 0:
+                    out_shape = shp
+                parts.append(t.contiguous())
+            return AG.attention(parts[0], parts[1], parts[2], self.scale, self.use_query_residual_pool), out_shape
         qkv5 = qkv.view(B, N, 3, h, C // h)
         # the three pooling launches are independent: K and V run on side streams next to Q so the small
         # deep-stage launches overlap instead of queueing (fork / join with events, graph-capturable)

@@ -219,6 +219,59 @@ def pool_qkv(qkv, heads, thw, descs, params):
     raise RuntimeError("pool_qkv is the training-path entry; inference uses attention.attention_pool directly")
 
 
+# ------------------------------------------------------------------------------------------------ generic pooling
+class _PoolHeads(Function):
+    """Pool3d of one [B, heads, L, d] operand (any strided view with unit channel stride) without cls token or LayerNorm:
+    mode "conv" (depthwise, weight [d,1,kt,kh,kw]), "avg" or "max".  The secondary variants of the reference
+    (MVIT.MODE avg / max, a cls token) are assembled from this, `layernorm` and plain tensor slicing / concatenation —
+    correct, on the generic kernels, not tuned (the shipped configs take the fused `_PoolQKV` path)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mode, thw, kernel, stride):
+        out, _ = ops.attention_pool_heads(x, list(thw), list(kernel), list(stride), mode=mode, weight=weight)
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (mode, list(thw), list(kernel), list(stride))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        mode, thw, kernel, stride = ctx.meta
+        B, heads, L, d = x.shape
+        dy = dy.to(x.dtype).contiguous()
+        xs = (x.stride(0), x.stride(2), x.stride(1))                   # (batch, token, head)
+        dxb = torch.empty((B, L, heads, d), dtype=x.dtype, device=x.device)
+        ds = (L * heads * d, heads * d, d)
+        dw = None
+        if mode == "max":
+            dx32 = torch.zeros((B, L, heads, d), dtype=torch.float32, device=x.device)
+            ops.attention_pool_bwd(3, x, xs, dy, None, dx32, None, B, heads, d, thw, kernel, stride)
+            dxb.copy_(dx32)
+        else:
+            taps = kernel[0] * kernel[1] * kernel[2]
+            if mode == "conv":
+                dw = torch.zeros((d, taps), dtype=torch.float32, device=x.device)
+                ops.attention_pool_bwd(1, x, xs, dy, None, None, dw, B, heads, d, thw, kernel, stride)
+                wmat = weight.reshape(d, -1)
+            else:                                                      # avg: count_include_pad -> every tap weighs 1/taps
+                wmat = torch.full((d, taps), 1.0 / taps, dtype=torch.float32, device=x.device)
+            ops.attention_pool_bwd(0, None, ds, dy, wmat, dxb, None, B, heads, d, thw, kernel, stride)
+        return dxb.permute(0, 2, 1, 3), _like_param(dw, weight), None, None, None, None
+
+
+def pool_heads_generic(t, thw, kernel, stride, mode, weight, ln, has_cls):
+    """Differentiable attention_pool of one [B, heads, L(+1), d] operand for the secondary variants."""
+    cls = None
+    if has_cls:
+        cls, t = t[:, :, :1], t[:, :, 1:]
+    out = _PoolHeads.apply(t, weight, mode, list(thw), list(kernel), list(stride))
+    if cls is not None:
+        out = torch.cat((cls, out), dim=2)
+    if ln is not None:
+        out = layernorm(out, ln[0], ln[1], ln[2])
+    return out, ops.pooled_thw(list(thw), kernel, stride)
+
+
 # ------------------------------------------------------------------------------------------------ skip-path max pool
 class _MaxPoolTokens(Function):
     @staticmethod
@@ -241,10 +294,13 @@ class _MaxPoolTokens(Function):
         return dx.to(x.dtype), None, None, None
 
 
-def maxpool_tokens(x, thw, kernel, stride):
+def maxpool_tokens(x, thw, kernel, stride, has_cls=False):
     if recording(x):
+        if has_cls:                                   # the cls row bypasses pooling (attention.py:28-29, 62-64)
+            pooled = _MaxPoolTokens.apply(x[:, 1:], thw, kernel, stride)
+            return torch.cat((x[:, :1], pooled), dim=1), ops.pooled_thw(list(thw), kernel, stride)
         return _MaxPoolTokens.apply(x, thw, kernel, stride), ops.pooled_thw(list(thw), kernel, stride)
-    return ops.attention_pool_tokens(x, list(thw), kernel, stride, mode="max")
+    return ops.attention_pool_tokens(x, list(thw), kernel, stride, mode="max", has_cls=has_cls)
 
 
 # ------------------------------------------------------------------------------------------------ patch embedding

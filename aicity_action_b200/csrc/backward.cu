@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const T *__restrict_
 struct PoolBwdParams {
   int64_t x_bs, x_ls, x_hs;            // strides of the pooling input / its gradient (elements)
   int B, heads, d, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo;
+  int dy_head_major;                   // max-pool gradient: dy is [B, heads, L', d] (1) or tokens [B, L', heads*d] (0)
 };
 
 // conv input gradient, gather form (deterministic): dx[pos] = sum over taps with (pos + pad - tap) % stride == 0 of
@@ -579,7 +580,8 @@ __global__ void __launch_bounds__(256) pool_max_bwd_kernel(const T *__restrict__
       }
     }
   }
-  const T *pdy = dy + (((int64_t)b * Lo + lo) * p.heads + head) * p.d;   // token layout [B, L', heads*d]
+  const T *pdy = p.dy_head_major ? dy + ((int64_t)(b * p.heads + head) * Lo + lo) * p.d
+                                 : dy + (((int64_t)b * Lo + lo) * p.heads + head) * p.d;   // token layout [B, L', heads*d]
   // dx is a dense fp32 [B, L, heads, d] buffer
 #pragma unroll
   for (int j = 0; j < NC; ++j)
@@ -769,11 +771,11 @@ extern "C" int mvit_attention_pool_bwd(int what, const void *x, int64_t x_bs, in
                                        const float *weight, void *dx, float *dw, int B, int heads, int d, int T, int H,
                                        int W, int kt, int kh, int kw, int st, int sh, int sw, int dtype, void *stream) {
   MVIT_REQUIRE(dy, "attention_pool_bwd: null pointer");
-  MVIT_REQUIRE(what >= 0 && what <= 2, "attention_pool_bwd: unknown gradient kind %d", what);
+  MVIT_REQUIRE(what >= 0 && what <= 3, "attention_pool_bwd: unknown gradient kind %d", what);
   MVIT_REQUIRE(d % 32 == 0 && d <= 128, "attention_pool_bwd: head_dim %d unsupported", d);
   MVIT_REQUIRE(kt * kh * kw <= 27, "attention_pool_bwd: kernel larger than 27 taps unsupported");
   MVIT_REQUIRE(dtype == MVIT_F32 || dtype == MVIT_BF16, "attention_pool_bwd: unknown dtype");
-  MVIT_REQUIRE((what == 0 && weight && dx) || (what == 1 && x && dw) || (what == 2 && x && dx), "attention_pool_bwd: missing operand");
+  MVIT_REQUIRE((what == 0 && weight && dx) || (what == 1 && x && dw) || (what >= 2 && x && dx), "attention_pool_bwd: missing operand");
   if (B == 0) return 0;
   PoolBwdParams p;
   p.x_bs = x_bs; p.x_ls = x_ls; p.x_hs = x_hs;
@@ -781,6 +783,8 @@ extern "C" int mvit_attention_pool_bwd(int what, const void *x, int64_t x_bs, in
   p.kt = kt; p.kh = kh; p.kw = kw; p.st = st; p.sh = sh; p.sw = sw;
   p.pt = kt / 2; p.ph = kh / 2; p.pw = kw / 2;
   p.To = (T + 2 * p.pt - kt) / st + 1; p.Ho = (H + 2 * p.ph - kh) / sh + 1; p.Wo = (W + 2 * p.pw - kw) / sw + 1;
+  p.dy_head_major = what == 3 ? 1 : 0;
+  if (what == 3) what = 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (what == 1) {
     PoolParams q{};

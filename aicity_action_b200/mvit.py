@@ -381,12 +381,17 @@ class MViT(nn.Module):
         T, H, W = self.patch_dims
         stem_params = [self.patch_embed.proj.weight, self.patch_embed.proj.bias]
         stem_params += [self.pos_embed_spatial, self.pos_embed_temporal] if self.sep_pos_embed else [self.pos_embed]
-        if AG.recording(*stem_params):
-            if not self.sep_pos_embed or self.cls_embed_on:
-                raise NotImplementedError("training is implemented for SEP_POS_EMBED without a cls token "
-                                          "(the Aicity configs)")
-            x = AG.patch_embed(self.patch_embed, x, dtype, self.pos_embed_spatial, self.pos_embed_temporal,
-                               self._pos_tokens(dtype))
+        if AG.recording(*stem_params, getattr(self, "cls_token", None)):
+            if self.sep_pos_embed and not self.cls_embed_on:
+                x = AG.patch_embed(self.patch_embed, x, dtype, self.pos_embed_spatial, self.pos_embed_temporal,
+                                   self._pos_tokens(dtype))
+            else:
+                # cls token / non-separable pos-embed (secondary variants): patch GEMM gradients through the same
+                # Function, concatenation and the positional add left to autograd
+                tokens = AG.patch_embed(self.patch_embed, x, dtype)
+                if self.cls_embed_on:
+                    tokens = torch.cat((self.cls_token.to(tokens.dtype).expand(tokens.shape[0], -1, -1), tokens), dim=1)
+                x = tokens + self._pos_table(dtype).to(tokens.dtype)
         elif self.sep_pos_embed and not self.cls_embed_on:
             # bias + positional embedding ride in the patch-embed GEMM epilogue
             pos = self._pos_tokens(dtype)

@@ -418,7 +418,7 @@ def attention_pool_bwd(what: int, x: Optional[torch.Tensor], strides: Tuple[int,
     _need_cuda(x, dy, weight, dx, dw)
     assert dy.is_contiguous()
     weight = _f32c(weight)
-    with _Timed(("pool_bwd_dgrad", "pool_bwd_wgrad", "pool_bwd_max")[what] + "_s%d" % stride[1], 0.0):
+    with _Timed(("pool_bwd_dgrad", "pool_bwd_wgrad", "pool_bwd_max", "pool_bwd_max")[what] + "_s%d" % stride[1], 0.0):
         check(_lib.load().mvit_attention_pool_bwd(what, _ptr(x), strides[0], strides[1], strides[2], _ptr(dy), _ptr(weight),
                                                   _ptr(dx), _ptr(dw), B, heads, d, thw[0], thw[1], thw[2], *kernel, *stride,
                                                   _dt(dy), _stream()), "mvit_attention_pool_bwd")

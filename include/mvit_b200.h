@@ -212,7 +212,8 @@ int mvit_attention_bwd(const void *q, const void *k, const void *v, const void *
  * (padding = kernel/2, no cls token):
  *   what 0: depthwise-conv input gradient, dx written through the forward's input strides (x_bs, x_ls, x_hs);
  *   what 1: depthwise-conv weight gradient dw[d, taps] += (x read through the strides);
- *   what 2: max-pool input gradient into a caller-zeroed dense fp32 dx [B, L, heads, d] (arg-max recomputed from x).
+ *   what 2: max-pool input gradient into a caller-zeroed dense fp32 dx [B, L, heads, d] (arg-max recomputed from x);
+ *   what 3: the same with dy laid out [B, heads, L', d] (max-pooled q / k / v of MVIT.MODE "max").
  * dy is the gradient w.r.t. the pooled (pre-LayerNorm) output: [B, heads, L', d] for what 0/1, token layout
  * [B, L', heads*d] for what 2 (the block's skip path pools [B, L, C] tokens). */
 int mvit_attention_pool_bwd(int what, const void *x, int64_t x_bs, int64_t x_ls, int64_t x_hs, const void *dy,

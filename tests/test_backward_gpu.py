@@ -402,3 +402,29 @@ def test_full_size_backward_kernels_cross_check():
     check("dw", dw_tc, dw_simt, 1e-3)
     check("db", db_tc, db_simt, 1e-3)
     check("db == column sums", db_tc, dy.float().sum(0), 1e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
+@pytest.mark.parametrize("mode,cls,sep", [("conv", True, True), ("max", True, False), ("avg", False, True)], ids=str)
+def test_secondary_variants_train(mode, cls, sep, dtype):
+    """cls token / MVIT.MODE avg, max / non-separable pos-embed: loss and every parameter gradient of the tiny model
+    against autograd through the oracle (these variants run on the generic differentiable pieces)."""
+    c = MODEL_CASES[0]
+    cfg, m, sd = _train_model(c, ["MVIT.CLS_EMBED_ON", cls, "MVIT.MODE", mode, "MVIT.SEP_POS_EMBED", sep])
+    x = synth_clip(c["seed"], c["B"], cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE)
+    labels = torch.arange(c["B"]) % cfg.MODEL.NUM_CLASSES
+    sdr = {k: leaf(v) for k, v in sd.items()}
+    loss_r = F.cross_entropy(O.mvit_forward(x, sdr, O.derive_spec(cfg), training=True), labels)
+    loss_r.backward()
+    loss = F.cross_entropy(m([x.cuda().to(dtype)]), labels.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_r.item()) < (1e-4 if dtype == torch.float32 else 2e-2) * max(1.0, abs(loss_r.item()))
+    l2 = dtype == torch.bfloat16
+    # max-pooled q/k/v: a near-tie decided differently by the two fp32 GEMMs (CPU vs CUDA summation order) re-routes one
+    # element's gradient, so MODE max gets 1e-3 instead of 1e-4 in fp32
+    tol = 1.5e-1 if l2 else (1e-3 if mode == "max" else 1e-4)
+    floor = grad_floor([sdr[k].grad for k, _ in m.named_parameters() if sdr[k].grad is not None])
+    for k, p in m.named_parameters():
+        if sdr[k].grad is None:                      # e.g. pos_embed_class-less configs
+            continue
+        check(k, p.grad, sdr[k].grad, tol, param_floor(k, floor), l2=l2)
