@@ -128,11 +128,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (warp == 3) {
+  if (warp >= 4) {
     // constant "ones" chunk of every V stage: [64 kv rows][32 cols] bf16, 64B-swizzled; logical column 0 = 1.0
+    // (written by the eight softmax warps, idle until the first scores arrive)
     for (int st = 0; st < kStages; ++st) {
       uint4 *chunk = reinterpret_cast<uint4 *>(sKV + st * kStageBytes + kKTileBytes + kChunks * kKChunkBytes);
-      for (int i = lane; i < kKChunkBytes / 16; i += 32) {
+      for (int i = threadIdx.x - 128; i < kKChunkBytes / 16; i += kThreads - 128) {
         const int r = i >> 2, c16 = i & 3;                       // row, physical 16-byte slot
         chunk[i] = make_uint4(c16 == ((r >> 1) & 3) ? 0x00003F80u : 0u, 0u, 0u, 0u);
       }
@@ -321,7 +322,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float inv = 1.0f / l_run;
       const int b = bh / p.heads, head = bh % p.heads;
       const bool live = row < p.Lq;
-      const bf16 *qrow = p.q + ((int64_t)bh * p.Lq + row) * D;
+      const int rl = quarter * 32 + lane;           // row inside the 128-row tile
+      if (p.add_q) mbar_wait(q_full, 0);            // acquire the TMA-written Q tile for the generic-proxy reads below
       bf16 *orow = p.out + (((int64_t)b * p.Lq + row) * p.heads + head) * D;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -333,7 +335,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int v4 = 0; v4 < 4; ++v4) {
             uint32_t w[4];
             uint4 qv = make_uint4(0, 0, 0, 0);
-            if (p.add_q) qv = *reinterpret_cast<const uint4 *>(qrow + c * 32 + v4 * 8);
+            // the pooled-q residual is still in shared memory (64B-swizzled: 16-byte slot ^ ((row >> 1) & 3))
+            if (p.add_q) qv = *reinterpret_cast<const uint4 *>(sQ + i * kQTileBytes + c * kQChunkBytes + rl * 64 +
+                                                              ((v4 ^ ((rl >> 1) & 3)) << 4));
             const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
