@@ -267,7 +267,8 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       mbar_wait(&dq_done[i], 0);
       tc_fence_after();
       bf16 *dqrow = p.dq + ((int64_t)bh * p.Lq + row) * D + colhalf * 48;
-      const bf16 *dorow = p.dout + (((int64_t)b * p.Lq + row) * p.heads + head) * D + colhalf * 48;
+      const int rl = quarter * 32 + lane;               // row inside the 128-row tile
+      if (p.add_q) mbar_wait(q_full, 0);                // acquire the TMA-written dO tile for the generic-proxy reads
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         uint32_t o[16];
@@ -278,7 +279,11 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           for (int v4 = 0; v4 < 2; ++v4) {
             uint32_t w[4];
             uint4 gv = make_uint4(0, 0, 0, 0);
-            if (p.add_q) gv = *reinterpret_cast<const uint4 *>(dorow + c * 16 + v4 * 8);
+            if (p.add_q) {                               // dO is still resident in shared memory (64B-swizzled chunks)
+              const int ch = colhalf * 48 + c * 16 + v4 * 8;
+              gv = *reinterpret_cast<const uint4 *>(sdO + i * kTile128 + (ch >> 5) * kChunk128 + rl * 64 +
+                                                    ((((ch & 31) >> 3) ^ ((rl >> 1) & 3)) << 4));
+            }
             const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
