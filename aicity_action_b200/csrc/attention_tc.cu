@@ -83,7 +83,7 @@ struct Params {
 template <int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, Params p) {
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sQ = smem;                                  // [2][24 KB]
@@ -324,20 +324,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const bool live = row < p.Lq;
       const int rl = quarter * 32 + lane;           // row inside the 128-row tile
       if (p.add_q) mbar_wait(q_full, 0);            // acquire the TMA-written Q tile for the generic-proxy reads below
-      bf16 *orow = p.out + (((int64_t)b * p.Lq + row) * p.heads + head) * D;
+      // The output tile is built IN PLACE over the Q tile in shared memory (each thread reads the pooled-q residual of
+      // its row from the slot it then overwrites; 64B-swizzled: 16-byte slot ^ ((row >> 1) & 3)) and leaves as three
+      // TMA stores into out[b, row0.., head, :] - coalesced, rows past Lq clipped by the tensor map.
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         uint32_t o[32];
         tmem_ld32(tO + c * 32, o);
         tmem_ld_wait();
-        if (live) {
+        {
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
             uint32_t w[4];
+            uint4 *slot = reinterpret_cast<uint4 *>(sQ + i * kQTileBytes + c * kQChunkBytes + rl * 64 +
+                                                    ((v4 ^ ((rl >> 1) & 3)) << 4));
             uint4 qv = make_uint4(0, 0, 0, 0);
-            // the pooled-q residual is still in shared memory (64B-swizzled: 16-byte slot ^ ((row >> 1) & 3))
-            if (p.add_q) qv = *reinterpret_cast<const uint4 *>(sQ + i * kQTileBytes + c * kQChunkBytes + rl * 64 +
-                                                              ((v4 ^ ((rl >> 1) & 3)) << 4));
+            if (p.add_q) qv = *slot;
             const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -348,11 +350,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
               w[e] = *reinterpret_cast<uint32_t *>(&h);
             }
-            *reinterpret_cast<uint4 *>(orow + c * 32 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            *slot = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
       if (p.lse && live) p.lse[(int64_t)bh * p.Lq + row] = (m_used + log2f(l_run)) * 0.69314718055994530942f;
+      fence_proxy_async_smem();                       // generic-proxy writes of the tile -> visible to the TMA store
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + i) : "memory");   // the 128 threads of this stream
+      if (quarter == 0 && lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          tma_store_4d(&tmap_o, sQ + i * kQTileBytes + c * kQChunkBytes, c * kChunkCols, head, q0 + i * BQ, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();                      // shared memory is released when the CTA exits
+      }
     }
   }
   tc_fence_before();
@@ -370,7 +381,7 @@ bool attention_tc_supported(const AttnArgs &a, const char **why) {
 }
 
 int attention_tc(const AttnArgs &a, cudaStream_t st) {
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   const int BH = a.B * a.heads;
   auto enc = [&](CUtensorMap *m, const void *ptr, int L, int box_rows) {
     const uint64_t dims[3] = {(uint64_t)attn::D, (uint64_t)L, (uint64_t)BH};
@@ -382,6 +393,12 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
   if ((r = enc(&tq, a.q, a.Lq, attn::BQ))) return r;
   if ((r = enc(&tk, a.k, a.Lk, attn::BKV))) return r;
   if ((r = enc(&tv, a.v, a.Lk, attn::BKV))) return r;
+  {   // out [B, Lq, heads, 96]: box = one stream's [128 rows x 32 cols] chunk of one head
+    const uint64_t dims[4] = {(uint64_t)attn::D, (uint64_t)a.heads, (uint64_t)a.Lq, (uint64_t)a.B};
+    const uint64_t strides[3] = {(uint64_t)attn::D * 2, (uint64_t)a.heads * attn::D * 2, (uint64_t)a.Lq * a.heads * attn::D * 2};
+    const uint32_t box[4] = {attn::kChunkCols, 1, attn::BQ, 1};
+    if ((r = encode_tmap_bf16(&to, a.out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+  }
   static int poly = -1;
   if (poly < 0) {
     const char *e = getenv("MVIT_ATTN_POLY");      // tuning knob; default: a quarter of the exponentials on the FMA pipe
@@ -394,9 +411,9 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
   attn::Params p{static_cast<const bf16 *>(a.q), static_cast<bf16 *>(a.out), a.lse, a.heads, a.Lq, a.Lk, a.add_q,
                  a.scale * 1.44269504088896340736f};
   dim3 grid((unsigned)((a.Lq + 2 * attn::BQ - 1) / (2 * attn::BQ)), (unsigned)BH);
-  if (poly == 0) attn::attention_tc_kernel<0><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
-  else if (poly == 2) attn::attention_tc_kernel<2><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
-  else attn::attention_tc_kernel<1><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, p);
+  if (poly == 0) attn::attention_tc_kernel<0><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, to, p);
+  else if (poly == 2) attn::attention_tc_kernel<2><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, to, p);
+  else attn::attention_tc_kernel<1><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, to, p);
   MVIT_LAUNCH_OK("attention(tcgen05)");
   return 0;
 }
