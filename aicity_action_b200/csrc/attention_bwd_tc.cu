@@ -104,7 +104,7 @@ struct DqParams {
 __global__ void __launch_bounds__(dq::kThreads, 1)
 attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                         const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                        DqParams p) {
+                        const __grid_constant__ CUtensorMap tmap_dq, DqParams p) {
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -263,10 +263,11 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tc_fence_before();
         mbar_arrive(&ds_ready[i]);
       }
-      // ---- epilogue: dQ = scale * acc (+ dO); colhalf 0 stores channels 0..47, colhalf 1 channels 48..95
+      // ---- epilogue: dQ = scale * acc (+ dO); colhalf 0 handles channels 0..47, colhalf 1 channels 48..95.  The tile is
+      // assembled over the (no longer needed) Q tile in shared memory, in the same 64B-swizzled chunk layout, and leaves
+      // as three TMA stores (coalesced; rows past Lq are clipped by the tensor map).
       mbar_wait(&dq_done[i], 0);
       tc_fence_after();
-      bf16 *dqrow = p.dq + ((int64_t)bh * p.Lq + row) * D + colhalf * 48;
       const int rl = quarter * 32 + lane;               // row inside the 128-row tile
       if (p.add_q) mbar_wait(q_full, 0);                // acquire the TMA-written dO tile for the generic-proxy reads
 #pragma unroll
@@ -274,27 +275,32 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         uint32_t o[16];
         tmem_ld16(tdQ + colhalf * 48 + c * 16, o);
         tmem_ld_wait();
-        if (live) {
 #pragma unroll
-          for (int v4 = 0; v4 < 2; ++v4) {
-            uint32_t w[4];
-            uint4 gv = make_uint4(0, 0, 0, 0);
-            if (p.add_q) {                               // dO is still resident in shared memory (64B-swizzled chunks)
-              const int ch = colhalf * 48 + c * 16 + v4 * 8;
-              gv = *reinterpret_cast<const uint4 *>(sdO + i * kTile128 + (ch >> 5) * kChunk128 + rl * 64 +
-                                                    ((((ch & 31) >> 3) ^ ((rl >> 1) & 3)) << 4));
-            }
-            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        for (int v4 = 0; v4 < 2; ++v4) {
+          uint32_t w[4];
+          const int ch = colhalf * 48 + c * 16 + v4 * 8;
+          const uint32_t off = (ch >> 5) * kChunk128 + rl * 64 + ((((ch & 31) >> 3) ^ ((rl >> 1) & 3)) << 4);
+          uint4 gv = make_uint4(0, 0, 0, 0);
+          if (p.add_q) gv = *reinterpret_cast<const uint4 *>(sdO + i * kTile128 + off);   // dO, still resident
+          const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = fmaf(__uint_as_float(o[v4 * 8 + 2 * e]), p.scale, __uint_as_float(gw[e] << 16));
-              const float hi = fmaf(__uint_as_float(o[v4 * 8 + 2 * e + 1]), p.scale, __uint_as_float(gw[e] & 0xffff0000u));
-              __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-              w[e] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            *reinterpret_cast<uint4 *>(dqrow + c * 16 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 4; ++e) {
+            const float lo = fmaf(__uint_as_float(o[v4 * 8 + 2 * e]), p.scale, __uint_as_float(gw[e] << 16));
+            const float hi = fmaf(__uint_as_float(o[v4 * 8 + 2 * e + 1]), p.scale, __uint_as_float(gw[e] & 0xffff0000u));
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            w[e] = *reinterpret_cast<uint32_t *>(&h);
           }
+          *reinterpret_cast<uint4 *>(sQ + i * kTile128 + off) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 256;" ::"r"(9 + i) : "memory");    // the 256 threads of this stream
+      if (quarter == 0 && colhalf == 0 && lane == 0) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+          tma_store_3d(&tmap_dq, sQ + i * kTile128 + c * kChunk128, c * kChunkCols, q0 + i * BQ, bh);
+        tma_store_commit();
+        tma_store_wait_all<0>();
       }
     }
   }
@@ -578,10 +584,12 @@ int attention_bwd_tc(const AttnBwdArgs &a, cudaStream_t st) {
     if ((r = enc_do(&tdo, dq::BQ))) return r;
     if ((r = enc3(&tk, a.k, a.Lk, dq::BKV))) return r;
     if ((r = enc3(&tv, a.v, a.Lk, dq::BKV))) return r;
+    CUtensorMap tdq;
+    if ((r = enc3(&tdq, a.dq, a.Lq, dq::BQ))) return r;
     DqParams p{static_cast<const bf16 *>(a.dout), static_cast<bf16 *>(a.dq), delta, lse2, a.heads, a.Lq, Lq_pad, a.Lk,
                a.add_q, a.scale, scale_log2};
     dim3 grid((unsigned)((a.Lq + 2 * dq::BQ - 1) / (2 * dq::BQ)), (unsigned)BH);
-    attention_bwd_dq_kernel<<<grid, dq::kThreads, dq::kSmemBytes, st>>>(tq, tdo, tk, tv, p);
+    attention_bwd_dq_kernel<<<grid, dq::kThreads, dq::kSmemBytes, st>>>(tq, tdo, tk, tv, tdq, p);
     MVIT_LAUNCH_OK("attention_bwd(dq)");
   }
   {
