@@ -272,7 +272,7 @@ def test_mvit_loss_and_gradients(c, dtype):
     loss.backward()
     assert abs(loss.item() - loss_r.item()) < (1e-4 if dtype == torch.float32 else 2e-2) * max(1.0, abs(loss_r.item()))
     # fp32 is the exactness proof (rel-inf 1e-4 on every parameter gradient).  bf16 is judged in the 2-norm (see
-    # test_block_bwd): roundings compound through four blocks forward and backward (tools/grad_report.py prints the table).
+    # test_block_bwd): roundings compound through four blocks forward and backward (tests/grad_report.py prints the table).
     l2 = dtype == torch.bfloat16
     # yardstick: PyTorch's own bf16 evaluation of the reference graph (CPU) deviates from its fp32 gradients by 1e-2 (head)
     # to 1.1e-1 (block 0 / patch embed) rel-l2 on this model; the CUDA path measures 2e-3 .. 9e-2.
