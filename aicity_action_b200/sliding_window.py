@@ -126,8 +126,8 @@ class SlidingWindowRunner:
     def local_scores(self, video, windows: List[Tuple[int, int]]) -> Tuple[List[int], torch.Tensor]:
         """Scores of this rank's windows: (window ids, [n_local, classes] float32 on CPU).
 
-        On a device the batches are pipelined: a host thread gathers and pins the uint8 frames of batch i+1 while batch i
-        runs, uploads go through a copy stream into one of two device buffers, and the per-batch probabilities stay on
+        On a device the batches are pipelined: host threads gather and pin the uint8 frames of the next batches while
+        batch i runs, uploads go through a copy stream into one of two device buffers, and the per-batch probabilities stay on
         the device until the video is done (one synchronisation per video instead of one per batch)."""
         mine = shard_windows(len(windows), self.rank, self.world)
         chunks = [mine[b0:b0 + self.batch_size] for b0 in range(0, len(mine), self.batch_size)]
@@ -143,16 +143,20 @@ class SlidingWindowRunner:
                 outs.append(self.model([clip]).float().cpu())
             return mine, (torch.cat(outs) if outs else torch.zeros((0, 0)))
 
-        import queue
-        import threading
-        q: "queue.Queue" = queue.Queue(maxsize=2)
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        # two host threads gather + pin batches ahead of the GPU (torch releases the GIL inside the copies); results are
+        # consumed in submission order
+        workers = ThreadPoolExecutor(max_workers=2)
+        pending, todo = deque(), iter(chunks)
 
-        def producer():
-            for ids in chunks:
-                q.put(host_batch(ids).pin_memory())
-            q.put(None)
+        def submit_next():
+            ids = next(todo, None)
+            if ids is not None:
+                pending.append(workers.submit(lambda ids=ids: host_batch(ids).pin_memory()))
 
-        threading.Thread(target=producer, daemon=True).start()
+        for _ in range(3):
+            submit_next()
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -171,10 +175,9 @@ class SlidingWindowRunner:
         for ev in freed:
             ev.record(cur)
         outs, i = [], 0
-        while True:
-            frames = q.get()
-            if frames is None:
-                break
+        while pending:
+            frames = pending.popleft().result()
+            submit_next()
             full = frames.shape[0] == self.batch_size
             slot = i % 2
             with torch.cuda.stream(copy):
@@ -198,6 +201,7 @@ class SlidingWindowRunner:
             freed[slot].record(cur)
             outs.append(probs.float())
             i += 1
+        workers.shutdown(wait=False)
         scores = torch.cat(outs).cpu() if outs else torch.zeros((0, 0))
         return mine, scores
 
