@@ -123,3 +123,11 @@ def test_install_into_reference_checkout():
     finally:
         ref_build.MODEL_REGISTRY._obj_map["MViT"] = saved[0]
         ref_attn.attention_pool, ref_attn.MultiScaleAttention, ref_attn.MultiScaleBlock = saved[1:]
+
+
+def test_graphed_forward_refuses_cpu_input():
+    from aicity_action_b200.graphed import GraphedForward
+    c = MODEL_CASES[0]
+    m = MViT(aicity_cfg(c["yaml"], tiny_cfg_overrides(c))).eval()
+    with pytest.raises(_lib.MvitLibraryError):
+        GraphedForward(m, torch.zeros(1, 3, 8, 64, 64))
