@@ -131,3 +131,52 @@ def test_graphed_forward_refuses_cpu_input():
     m = MViT(aicity_cfg(c["yaml"], tiny_cfg_overrides(c))).eval()
     with pytest.raises(_lib.MvitLibraryError):
         GraphedForward(m, torch.zeros(1, 3, 8, 64, 64))
+
+
+def test_patch_embed_fold_geometry_equals_conv3d():
+    """Host logic of the implicit-GEMM patch embedding: space-to-depth fold of the clip + the Conv3d weight scattered into
+    the folded layout (PatchEmbed._folded_weight) reproduce F.conv3d exactly (fp32 emulation of what the kernel sums)."""
+    import torch.nn.functional as F
+    from aicity_action_b200.mvit import PatchEmbed
+    torch.manual_seed(0)
+    pe = PatchEmbed(dim_in=3, dim_out=16, kernel=(3, 7, 7), stride=(2, 4, 4), padding=(1, 3, 3))
+    x = torch.randn(2, 3, 8, 32, 32)
+    ref = F.conv3d(x, pe.proj.weight, pe.proj.bias, stride=(2, 4, 4), padding=(1, 3, 3))     # [B, 16, 4, 8, 8]
+    k, s, p, lo, taps, creal, cf = pe._fold_geometry()
+    assert (taps, lo, creal, cf) == ([2, 2, 2], [-1, -1, -1], 96, 128)
+    B, C, T, H, W = x.shape
+    Tf, Hf, Wf = T // s[0], H // s[1], W // s[2]
+    # folded[b, t, h, w, ((ot*sh + oh)*sw + ow)*C + c] = x[b, c, t*st + ot, h*sh + oh, w*sw + ow]
+    f = x.view(B, C, Tf, s[0], Hf, s[1], Wf, s[2]).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, Tf, Hf, Wf, creal)
+    f = F.pad(f, (0, cf - creal))
+    wf = pe._folded_weight().float().view(16, taps[0], taps[1], taps[2], cf)     # bf16-rounded weights
+    wq = pe.proj.weight.detach().bfloat16().float()
+    ref_q = F.conv3d(x, wq, pe.proj.bias, stride=(2, 4, 4), padding=(1, 3, 3))
+    out = torch.zeros(B, Tf, Hf, Wf, 16)
+    fp = F.pad(f, (0, 0, 1, 1, 1, 1, 1, 1))            # one folded block of zero padding on every side
+    for a in range(taps[0]):
+        for b in range(taps[1]):
+            for c in range(taps[2]):
+                dt, dh, dw = lo[0] + a, lo[1] + b, lo[2] + c
+                sl = fp[:, 1 + dt:1 + dt + Tf, 1 + dh:1 + dh + Hf, 1 + dw:1 + dw + Wf]
+                out += torch.einsum("bthwc,nc->bthwn", sl, wf[:, a, b, c])
+    out = out + pe.proj.bias.detach()
+    assert torch.allclose(out.permute(0, 4, 1, 2, 3), ref_q, atol=1e-4)
+    assert (out.permute(0, 4, 1, 2, 3) - ref).abs().max() < 5e-2        # only the bf16 rounding of the weights apart
+
+
+def test_drop_path_scale_consumes_rng_like_the_reference():
+    """common.py:46-59: mask = floor(keep + rand([B,1,1])); x / keep * mask — same draw, same values."""
+    from aicity_action_b200.common import drop_path_scale
+    B, p = 6, 0.3
+    torch.manual_seed(123)
+    s = drop_path_scale(B, p, True, torch.device("cpu"))
+    torch.manual_seed(123)
+    keep = 1 - p
+    mask = keep + torch.rand((B, 1, 1), dtype=torch.float32)
+    mask.floor_()
+    x = torch.ones(B, 1, 1)
+    ref = (x.div(keep) * mask).reshape(B)
+    assert torch.equal(s, ref)
+    assert drop_path_scale(B, 0.0, True, torch.device("cpu")) is None
+    assert drop_path_scale(B, p, False, torch.device("cpu")) is None
