@@ -88,3 +88,34 @@ def test_shard_is_a_partition():
     for n, w in [(1125, 8), (7, 4), (0, 2), (33, 2)]:
         parts = [SW.shard_windows(n, r, w) for r in range(w)]
         assert sorted(sum(parts, [])) == list(range(n))
+
+
+def test_randomised_window_logic_matches_oracle():
+    """Bit-exact host logic on random cases (the golden fixtures pin the oracle to the reference; this pins the product to
+    the oracle away from the fixture sizes): window lists incl. short / ragged videos, frame indices, fps adjustment,
+    chunking at random thresholds, mean / max aggregation over overlapping windows."""
+    import window_oracle as WO
+    rng = np.random.RandomState(7)
+    for _ in range(60):
+        n = int(rng.randint(1, 4000))
+        length, stride = int(rng.choice([32, 48, 64, 96])), int(rng.choice([8, 16, 24, 64]))
+        assert SW.window_list(n, length, stride) == WO.window_list(n, length, stride)
+        fps = float(rng.choice([15.0, 24.0, 25.0, 29.97, 30.0, 60.0]))
+        assert SW.fps_adjusted_window(length, stride, fps) == WO.fps_adjust(length, stride, fps, 30.0)
+        wl = WO.window_list(n, length, stride)
+        for t0, t1 in wl[:3] + wl[-3:]:
+            assert SW.frame_indices(t0, t1, 16, n) == WO.frame_indices(t0, t1, 16, n)
+    for _ in range(40):
+        m = int(rng.randint(1, 400))
+        scores = rng.rand(m).astype(np.float32)
+        scores[rng.rand(m) < 0.3] = 0.0
+        thr = float(rng.rand())
+        got = [(a, b, k, float(s)) for a, b, k, s, _ in PP.get_chunks(scores, thr)]
+        ref = [(a, b, k, float(s)) for a, b, k, s, *_ in WO.get_chunks(scores, thr)]
+        assert got == ref
+    for _ in range(10):
+        n = int(rng.randint(70, 900))
+        wl = WO.window_list(n, 64, 16)
+        preds = [(t0, t1, rng.rand(18).astype(np.float32)) for t0, t1 in wl]
+        assert np.array_equal(PP.aggregate_predictions(preds, np.mean, 18), WO.aggregate(preds, 18, "mean"))
+        assert np.array_equal(PP.aggregate_predictions(preds, np.max, 18), WO.aggregate(preds, 18, "max"))
