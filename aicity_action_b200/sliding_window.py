@@ -79,9 +79,17 @@ class SyntheticVideo:
     def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
         """[T, S, S, 3] uint8: one gather from the (lazily built) texture pool, so that host-side frame synthesis does not
         bound the benchmark the way a Python loop over frames did."""
+        return self._textures()[torch.as_tensor([int(i) % self.PERIOD for i in idxs])]
+
+    def _textures(self) -> torch.Tensor:
         if self._pool is None:
             self._pool = torch.stack([self._texture(k) for k in range(self.PERIOD)])
-        return self._pool[torch.as_tensor([int(i) % self.PERIOD for i in idxs])]
+        return self._pool
+
+    def get_batch_into(self, idxs: Sequence[int], out: torch.Tensor) -> None:
+        """Same frames as `get_batch`, written straight into `out` ([T, S, S, 3] uint8, e.g. a slice of a pinned staging
+        buffer): one copy per frame instead of gather + stack + pin."""
+        torch.index_select(self._textures(), 0, torch.as_tensor([int(i) % self.PERIOD for i in idxs]), out=out)
 
 
 # ----------------------------------------------------------------------------- the runner
@@ -102,7 +110,7 @@ class SlidingWindowRunner:
     def __init__(self, model: Callable, num_frames: int = 16, sampling_rate: int = 4, proposal_stride: int = 16,
                  batch_size: int = 8, dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
                  rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None,
-                 use_cuda_graph: bool = False):
+                 use_cuda_graph: bool = False, host_threads: int = 3, n_stage: int = 4):
         self.model, self.T, self.rate = model, num_frames, sampling_rate
         self.length, self.stride = num_frames * sampling_rate, proposal_stride   # run_action...py:76
         self.batch_size, self.dtype, self.device = batch_size, dtype, device
@@ -111,6 +119,8 @@ class SlidingWindowRunner:
         self._graphed = [None, None]
         self._dbuf = [None, None]
         self._copy_stream = None
+        self.host_threads, self.n_stage = max(1, host_threads), max(2, n_stage)
+        self._stage, self._stage_free = None, None
         if preprocess is None and device is not None and dtype != torch.bfloat16:
             from . import ops
             preprocess = lambda u8: ops.preprocess_u8(u8, dtype)
@@ -145,31 +155,59 @@ class SlidingWindowRunner:
 
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
-        # two host threads gather + pin batches ahead of the GPU (torch releases the GIL inside the copies); results are
-        # consumed in submission order
-        workers = ThreadPoolExecutor(max_workers=2)
-        pending, todo = deque(), iter(chunks)
-
-        def submit_next():
-            ids = next(todo, None)
-            if ids is not None:
-                pending.append(workers.submit(lambda ids=ids: host_batch(ids).pin_memory()))
-
-        for _ in range(3):
-            submit_next()
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         copy = self._copy_stream
-        # the two upload buffers live as long as the runner: the captured graphs read them by address, and a buffer
-        # allocated mid-stream could be a block that kernels already in flight on the compute stream are still using
-        if chunks and len(chunks[0]) == self.batch_size:
-            shape = (self.batch_size, self.T) + tuple(video.get_batch([0]).shape[1:])
-            if self._dbuf[0] is None or tuple(self._dbuf[0].shape) != shape:
-                cur.synchronize()
-                self._dbuf = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
-                self._graphed = [None, None]
-        dbuf = self._dbuf
+        frame_shape = tuple(video.get_batch([0]).shape[1:])
+        shape = (self.batch_size, self.T) + frame_shape
+        # Device side: two upload buffers that live as long as the runner (the captured graphs read them by address, and a
+        # buffer allocated mid-stream could be a block that kernels in flight on the compute stream still use).  Host side:
+        # a ring of pinned staging buffers that the worker threads fill in place (`get_batch_into`): no per-batch
+        # cudaHostAlloc, one memcpy per frame.
+        if self._dbuf[0] is None or tuple(self._dbuf[0].shape) != shape:
+            cur.synchronize()
+            self._dbuf = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._stage = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(self.n_stage)]
+            self._stage_free = [torch.cuda.Event() for _ in range(self.n_stage)]
+            self._graphed = [None, None]
+        dbuf, stage, stage_free = self._dbuf, self._stage, self._stage_free
+        if self.use_cuda_graph and chunks and len(chunks[0]) == self.batch_size:
+            # capture BEFORE any worker thread exists: CUDA calls from other threads during a global-mode stream capture
+            # (cudaHostAlloc, event queries) can invalidate it
+            from .graphed import GraphedForward
+            for slot in range(2):
+                if self._graphed[slot] is None:
+                    pool = next((g.pool for g in self._graphed if g is not None), None)
+                    dbuf[slot].zero_()
+                    self._graphed[slot] = GraphedForward(self.model, dbuf[slot], pool=pool)
+        into = getattr(video, "get_batch_into", None)
+
+        def fill(j, ids):
+            """Worker thread: gather the frames of batch j into staging buffer j % n_stage once its last upload is done."""
+            k = j % self.n_stage
+            stage_free[k].synchronize()
+            buf = stage[k][:len(ids)]
+            for n, w in enumerate(ids):
+                idxs = frame_indices(*windows[w], self.T, len(video))
+                if into is not None:
+                    into(idxs, buf[n])
+                else:
+                    buf[n].copy_(torch.as_tensor(video.get_batch(idxs)))
+            return buf
+
+        workers = ThreadPoolExecutor(max_workers=self.host_threads)
+        pending, todo = deque(), iter(enumerate(chunks))
+
+        def submit_next():
+            nxt = next(todo, None)
+            if nxt is not None:
+                pending.append(workers.submit(fill, *nxt))
+
+        for ev in stage_free:
+            ev.record(cur)
+        for _ in range(self.n_stage - 1):
+            submit_next()
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
         for ev in freed:
@@ -177,31 +215,27 @@ class SlidingWindowRunner:
         outs, i = [], 0
         while pending:
             frames = pending.popleft().result()
-            submit_next()
             full = frames.shape[0] == self.batch_size
             slot = i % 2
             with torch.cuda.stream(copy):
                 copy.wait_event(freed[slot])
-                dev_frames = dbuf[slot] if full else torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
+                dev_frames = dbuf[slot][:frames.shape[0]]
                 dev_frames.copy_(frames, non_blocking=True)
                 ready[slot].record(copy)
+                stage_free[i % self.n_stage].record(copy)
+            submit_next()
             cur.wait_event(ready[slot])
             if self.use_cuda_graph and full:
                 # full batches replay a captured graph per upload buffer (uint8 frames in, normalisation fused into the
                 # patch embed); the ragged last batch takes the eager path
-                if self._graphed[slot] is None:
-                    from .graphed import GraphedForward
-                    pool = next((g.pool for g in self._graphed if g is not None), None)
-                    self._graphed[slot] = GraphedForward(self.model, dbuf[slot], pool=pool)
                 probs = self._graphed[slot]().clone()
             else:
                 clip = self.preprocess(dev_frames) if self.preprocess is not None else dev_frames
                 probs = self.model([clip])
-                dev_frames.record_stream(cur)
             freed[slot].record(cur)
             outs.append(probs.float())
             i += 1
-        workers.shutdown(wait=False)
+        workers.shutdown(wait=True)
         scores = torch.cat(outs).cpu() if outs else torch.zeros((0, 0))
         return mine, scores
 

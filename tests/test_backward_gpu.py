@@ -282,6 +282,41 @@ def test_mvit_loss_and_gradients(c, dtype):
         check(k, p.grad, sdr[k].grad, tol, param_floor(k, floor), l2=l2)
 
 
+@pytest.mark.parametrize("c", MODEL_CASES[:2], ids=lambda c: c["name"])
+def test_mvit_bf16_gradients_no_worse_than_reference_bf16(c):
+    """The bf16 yardstick, measured in the test instead of quoted in a comment: the reference graph evaluated by stock
+    PyTorch in bf16 on this GPU (`ref16`) and the CUDA path in bf16 (`ours16`) are both compared with the reference graph
+    in fp32 (`ref32`).  For every parameter the CUDA path must be as close to the fp32 gradients as the reference's own bf16
+    run is (rel-l2, 1.5x slack + 1e-2 floor), and its worst parameter must not be worse than the reference's worst."""
+    cfg, m, sd = _train_model(c)
+    x = synth_clip(c["seed"], c["B"], cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda()
+    labels = (torch.arange(c["B"]) % cfg.MODEL.NUM_CLASSES).cuda()
+    spec = O.derive_spec(cfg)
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd32 = {k: leaf(v, None, True) for k, v in sd.items()}
+        F.cross_entropy(O.mvit_forward(x, sd32, spec, training=True), labels).backward()
+        sd16 = {k: leaf(v, torch.bfloat16, True) for k, v in sd.items()}
+        F.cross_entropy(O.mvit_forward(x.bfloat16(), sd16, spec, training=True).float(), labels).backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    F.cross_entropy(m([x.bfloat16()]), labels).backward()
+    floor = grad_floor([sd32[k].grad for k, _ in m.named_parameters()])
+    worst_ours, worst_ref, rows = 0.0, 0.0, []
+    for k, p in m.named_parameters():
+        r32 = sd32[k].grad.float()
+        den = max(r32.norm().item(), param_floor(k, floor) * r32.numel() ** 0.5, 1e-30)
+        e_ours = (p.grad.float() - r32).norm().item() / den
+        e_ref = (sd16[k].grad.float() - r32).norm().item() / den
+        rows.append((k, e_ours, e_ref))
+        worst_ours, worst_ref = max(worst_ours, e_ours), max(worst_ref, e_ref)
+    bad = [(k, a, b) for k, a, b in rows if a > 1.5 * b + 1e-2]
+    print(f"bf16 gradient rel-l2 vs fp32 reference: worst ours {worst_ours:.3e}, worst reference-bf16 {worst_ref:.3e}")
+    assert not bad, bad[:5]
+    assert worst_ours <= 1.25 * worst_ref + 1e-2
+
+
 def test_activation_checkpoint_matches_plain():
     c = MODEL_CASES[0]
     cfg, m, _ = _train_model(c)
