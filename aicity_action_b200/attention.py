@@ -23,12 +23,38 @@ from . import ops
 from .common import DropPath, Mlp, drop_path_scale
 
 
+_COMPUTE_POLICY = None       # None: read $MVIT_B200_COMPUTE at call time; else "auto" | "bf16" | "fp32"
+
+
+def set_compute_dtype(policy):
+    """Arithmetic used for fp32 input tensors: "auto" (fp32 kernels unless a 16-bit autocast region is active — the
+    reference's own contract), "bf16" (bf16 storage + tcgen05 kernels, as if the call sat in a bf16 autocast region; what
+    the reference's inference scripts need to reach the tensor cores: they pass fp32 clips with no autocast,
+    scripts/module_wrapper.py:606-608), "fp32" (fp32 kernels even under autocast).  None re-enables $MVIT_B200_COMPUTE."""
+    global _COMPUTE_POLICY
+    if policy not in (None, "auto", "bf16", "fp32"):
+        raise ValueError(f"compute dtype policy must be auto, bf16 or fp32, got {policy!r}")
+    _COMPUTE_POLICY = policy
+
+
+def compute_policy() -> str:
+    import os
+    pol = _COMPUTE_POLICY or os.environ.get("MVIT_B200_COMPUTE", "auto").lower()
+    if pol not in ("auto", "bf16", "fp32"):
+        raise ValueError(f"MVIT_B200_COMPUTE must be auto, bf16 or fp32, got {pol!r}")
+    return pol
+
+
 def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     """fp32 tensors run the fp32 kernels unless a bf16 autocast region is active (the reference's
-    TRAIN.MIXED_PRECISION / torch.autocast contract); bf16 tensors run the tensor-core kernels."""
+    TRAIN.MIXED_PRECISION / torch.autocast contract) or the compute policy says bf16; bf16 tensors run the
+    tensor-core kernels."""
     if x.dtype == torch.bfloat16 or x.dtype == torch.uint8:     # uint8 = raw frames, normalised on the device
         return torch.bfloat16
     if x.dtype == torch.float32:
+        pol = compute_policy()
+        if pol != "auto":
+            return torch.bfloat16 if pol == "bf16" else torch.float32
         # any reduced-precision autocast region selects the tensor-core path; fp16 autocast (what the reference's
         # `torch.cuda.amp.autocast(enabled=TRAIN.MIXED_PRECISION)` requests, train_net.py:126) is served in bf16:
         # same 16-bit storage, wider exponent, so the GradScaler that accompanies it is harmless

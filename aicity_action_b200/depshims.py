@@ -129,8 +129,10 @@ class Registry:
 
 
 class _PathManager:
-    def open(self, path, mode="r", **kw):
-        return open(path, mode)
+    def open(self, path, mode="r", buffering=-1, **kw):
+        if any(c in mode for c in "wa") and os.path.dirname(path):
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+        return open(path, mode, buffering=buffering)
 
     def exists(self, p):
         return os.path.exists(p)
@@ -236,14 +238,25 @@ _STUB_ROOTS = (
 
 _ACTIVE_ROOTS = ()
 
+
+def _simplejson_dumps(obj, use_decimal=False, **kw):
+    """simplejson.dumps: Decimal values are written as plain numbers (the reference logs them, slowfast/utils/logging.py:97)."""
+    import decimal
+
+    def default(o):
+        if isinstance(o, decimal.Decimal):
+            return float(o)
+        raise TypeError(f"Object of type {type(o).__name__} is not JSON serializable")
+
+    return json.dumps(obj, default=default, **kw)
+
 _SPECIAL = {
     "fvcore.common.config": {"CfgNode": CfgNode},
     "fvcore.common.registry": {"Registry": Registry},
     "fvcore.common.timer": {"Timer": _Timer},
     "iopath.common.file_io": {"PathManagerFactory": _PathManagerFactory, "g_pathmgr": _PathManager()},
     "fairscale.nn.checkpoint": {"checkpoint_wrapper": _checkpoint_wrapper},
-    "simplejson": {"dumps": lambda o, **k: json.dumps(o, **{kk: v for kk, v in k.items() if kk != "use_decimal"}),
-                   "loads": json.loads},
+    "simplejson": {"dumps": lambda o, **k: _simplejson_dumps(o, **k), "loads": json.loads},
 }
 
 

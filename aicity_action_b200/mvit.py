@@ -275,10 +275,12 @@ class MViT(nn.Module):
 
         self.norm_stem = norm_layer(embed_dim) if cfg.MVIT.NORM_STEM else None
         self.act_checkpoint = bool(cfg.MODEL.ACT_CHECKPOINT)
-        # MODEL.ACT_CHECKPOINT trades a second forward for activation memory.  The fused path never stores a score
-        # matrix, so a clip @448 keeps ~1.6 GB of bf16 activations: on a 180 GB B200 the flag is honoured only when the
-        # estimate does not fit the free memory ("auto"); MVIT_B200_ACT_CHECKPOINT=always|never overrides.
-        self.act_checkpoint_policy = os.environ.get("MVIT_B200_ACT_CHECKPOINT", "auto")
+        # MODEL.ACT_CHECKPOINT trades a second forward for activation memory and is honoured as written ("always": every
+        # block is recomputed in backward, as fairscale's checkpoint_wrapper does, video_model_builder.py:988-1036).  The
+        # fused path never stores a score matrix, so a clip @448 keeps only ~1.6 GB of bf16 activations: on a 180 GB B200
+        # MVIT_B200_ACT_CHECKPOINT=auto opts into recomputing only when the estimate does not fit the free memory (the
+        # decision is logged once per input shape); =never ignores the flag.
+        self.act_checkpoint_policy = os.environ.get("MVIT_B200_ACT_CHECKPOINT", "always")
         self._ckpt_decision = {}
 
         self.blocks = nn.ModuleList()
@@ -375,6 +377,10 @@ class MViT(nn.Module):
                 thw = new_thw
             free, _ = torch.cuda.mem_get_info(x.device)
             self._ckpt_decision[key] = est * 1.5 > free      # keep activations when they fit with 50 % headroom
+            import logging
+            logging.getLogger(__name__).info(
+                "MVIT_B200_ACT_CHECKPOINT=auto: estimated %.1f GB of activations, %.1f GB free -> %s", est / 2 ** 30,
+                free / 2 ** 30, "recompute blocks in backward" if self._ckpt_decision[key] else "keep activations")
         return self._ckpt_decision[key]
 
     def forward_features(self, x, dtype):

@@ -7,18 +7,22 @@
   `aicity_action_b200.mvit.MViT`, so `build_model(cfg)` constructs, `.cuda()`s and (NUM_GPUS > 1) DDP-wraps the drop-in;
 * `slowfast.models.attention.{attention_pool, MultiScaleAttention, MultiScaleBlock}` are rebound as well, so reference
   code that builds blocks directly (and the reference `MViT` class, if someone keeps it) gets the B200 modules.
-Everything else of the reference (configs, data loading, checkpoints, train/test loops) runs unchanged.
+Everything else of the reference (configs, data loading, checkpoints, train/test loops) runs unchanged;
+`python -m aicity_action_b200.launch <script> ...` (launch.py) does this for the reference's entry scripts.
 """
 from __future__ import annotations
 
 
-def install(replace_model: bool = True, replace_blocks: bool = True) -> dict:
-    """Returns {'registry': bool, 'attention': bool}: what was rebound.  Raises ImportError if `slowfast` is not importable."""
+def install(replace_model: bool = True, replace_blocks: bool = True, compute_dtype=None) -> dict:
+    """Returns {'registry': bool, 'attention': bool}: what was rebound.  Raises ImportError if `slowfast` is not importable.
+    `compute_dtype` ("auto" | "bf16" | "fp32" | None = leave $MVIT_B200_COMPUTE in charge): see attention.set_compute_dtype."""
     import importlib
 
     from . import attention as b200_attn
     from . import mvit as b200_mvit
 
+    if compute_dtype is not None:
+        b200_attn.set_compute_dtype(compute_dtype)
     done = {"registry": False, "attention": False}
     if replace_blocks:
         ref_attn = importlib.import_module("slowfast.models.attention")

@@ -92,6 +92,33 @@ class SyntheticVideo:
         torch.index_select(self._textures(), 0, torch.as_tensor([int(i) % self.PERIOD for i in idxs]), out=out)
 
 
+class ArrayVideo:
+    """Decoded RGB frames held in host memory ([N, H, W, 3] uint8 array or memmap) — what the reference's decord reader
+    yields.  `get_batch` resizes each requested frame the way the reference does before the cast to float: uint8
+    `cv2.resize(frame, (S, S), INTER_LINEAR)`, aspect ratio ignored (scripts/utils.py:207-211 with keep_scale=False,
+    module_wrapper.py:326-331), so the clips the model sees are bit-identical to the reference's."""
+
+    def __init__(self, frames, size: int, fps: float = 30.0):
+        self.frames, self.size, self.fps = frames, size, fps
+
+    def __len__(self):
+        return int(self.frames.shape[0])
+
+    def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
+        import cv2
+        out = np.empty((len(idxs), self.size, self.size, 3), dtype=np.uint8)
+        for n, i in enumerate(idxs):
+            f = np.asarray(self.frames[int(i)])
+            if f.shape[0] == self.size and f.shape[1] == self.size:
+                out[n] = f
+            else:
+                cv2.resize(f, (self.size, self.size), dst=out[n], interpolation=cv2.INTER_LINEAR)
+        return torch.from_numpy(out)
+
+    def get_batch_into(self, idxs: Sequence[int], out: torch.Tensor) -> None:
+        out.copy_(self.get_batch(idxs))
+
+
 # ----------------------------------------------------------------------------- the runner
 @dataclass
 class WindowPrediction:

@@ -413,6 +413,7 @@ def run_ours(args):
     # ---- secondary figure: one training step (forward + backward + AdamW) of the same model on the same clips, bf16
     # autocast as TRAIN.MIXED_PRECISION does, DistributedDataParallel over NCCL when world > 1 (build.py:44-53)
     ms_train, train_launches, train_steps = 0.0, 0, 0
+    train_variants = {}
     if not args.no_train:
         import torch.nn.functional as F
         # the reference's recipe (README.md:100-112): activation checkpointing, DropPath 0.4, head
@@ -426,33 +427,49 @@ def run_ours(args):
         labels = torch.randint(0, cfg.MODEL.NUM_CLASSES, (B,), device=dev)
         train_steps = max(2, min(K, 5))
 
-        def train_step():
-            loss = F.cross_entropy(net([dev_clip]).float(), labels)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-            opt.step()
-            return loss
+        def time_train(policy, clip, lab, steps, warm):
+            """`steps` timed optimisation steps (forward + backward + clip + AdamW) under one ACT_CHECKPOINT policy."""
+            model.act_checkpoint_policy = policy
 
-        torch.cuda.empty_cache()                     # inference-phase blocks go back before the allocator re-plans
-        for _ in range(3):
-            train_step()
-        barrier()
-        n0 = ops.launch_count
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(train_steps):
-            loss = train_step()
-        r1.record()
-        barrier()
-        ms_train = r0.elapsed_time(r1)
-        train_launches = ops.launch_count - n0
-        assert torch.isfinite(loss)
+            def train_step():
+                loss = F.cross_entropy(net([clip]).float(), lab)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                opt.step()
+                return loss
+
+            torch.cuda.empty_cache()                 # earlier phases' blocks go back before the allocator re-plans
+            for _ in range(warm):
+                train_step()
+            barrier()
+            n0 = ops.launch_count
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(steps):
+                loss = train_step()
+            r1.record()
+            barrier()
+            assert torch.isfinite(loss)
+            return r0.elapsed_time(r1), ops.launch_count - n0
+
+        # headline training figure = config 4 as written: MODEL.ACT_CHECKPOINT True honoured (every block recomputed)
+        ms_train, train_launches = time_train("always", dev_clip, labels, train_steps, 3)
+        # beside it: the same step keeping the activations (they fit in 180 GB), and the reference's own arithmetic for
+        # this config (TRAIN.MIXED_PRECISION False = fp32 tensors -> the fp32 CUDA-core kernels) on a 2-clip batch
+        ms_keep, _ = time_train("never", dev_clip, labels, train_steps, 2)
+        train_variants["bf16_keep_activations"] = (ms_keep, train_steps, B)
+        if not args.no_fp32_train:
+            ms_f32, _ = time_train("always", dev_clip[:2].float(), labels[:2], 1, 1)
+            train_variants["fp32_act_checkpoint"] = (ms_f32, 1, 2)
     ddp_check = ddp_grad_check(dev, rank, world, local) if (world > 1 and not args.no_train) else None
-    times = torch.tensor([ms, ms_e2e, ms_train], device=dev, dtype=torch.float64)
+    vkeys = sorted(train_variants)
+    times = torch.tensor([ms, ms_e2e, ms_train] + [train_variants[k][0] for k in vkeys], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_train = times.tolist()
+    ms, ms_e2e, ms_train = times.tolist()[:3]
+    for k, t in zip(vkeys, times.tolist()[3:]):
+        train_variants[k] = (t,) + train_variants[k][1:]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -497,10 +514,13 @@ def run_ours(args):
         line["train"] = {"value": world * B * train_steps / (ms_train * 1e-3), "unit": "clips/s",
                          "ms_per_step": ms_train / train_steps, "steps": train_steps, "batch_per_gpu": B,
                          "gpu_launches": train_launches,
-                         "what": "forward + backward (MODEL.ACT_CHECKPOINT True under the 'auto' policy: activations fit in HBM so "
-                                 "nothing is recomputed; DropPath 0.4, head dropout 0.5) + "
-                                 "grad-clip + AdamW, bf16 activations / fp32 master weights"
-                                 + (", DDP gradient all-reduce over NCCL" if world > 1 else "")}
+                         "what": "BASELINE config 4: forward + backward with MODEL.ACT_CHECKPOINT True honoured (every block "
+                                 "recomputed in backward), DropPath 0.4, head dropout 0.5, grad-clip 1.0, AdamW; bf16 "
+                                 "activations / fp32 master weights"
+                                 + (", DDP gradient all-reduce over NCCL" if world > 1 else ""),
+                         "variants": {k: {"value": world * nb * ns / (t * 1e-3), "unit": "clips/s", "ms_per_step": t / ns,
+                                          "steps": ns, "batch_per_gpu": nb}
+                                      for k, (t, ns, nb) in train_variants.items()}}
     if sw is not None:
         line["sliding_window"] = sw
     if ddp_check is not None:
@@ -544,6 +564,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--no-fp32-train", action="store_true", help="skip the fp32 training-step variant")
     ap.add_argument("--no-cuda-graph", action="store_true", help="issue every launch from Python instead of graph replay")
     ap.add_argument("--preheat", type=float, default=3.0, help="seconds of untimed steps before the timed region")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the sharded sliding-window leg (config 3)")
