@@ -25,6 +25,7 @@ SIGNATURES = {
     "mvit_abi_version": (_i, []),
     "mvit_last_error": (C.c_char_p, []),
     "mvit_device_supported": (_i, []),
+    "mvit_device_fault": (_i, []),
     "mvit_layernorm_fwd": (_i, [_p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "mvit_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _i, _p]),
     "mvit_im2col3d_fwd": (_i, [_p, _p] + [_i] * 16 + [_p]),
@@ -74,6 +75,15 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def device_fault_check():
+    """Synchronises the device and raises if a tensor-core kernel abandoned an mbarrier wait since the last call (its
+    results are invalid).  The kernels raise a device flag instead of trapping, so the CUDA context stays usable."""
+    n = load().mvit_device_fault()
+    if n != 0:
+        msg = load().mvit_last_error()
+        raise MvitLibraryError(f"device fault reported by libmvit_b200.so: {msg.decode() if msg else '?'}")
 
 
 def check(rc: int, what: str):

@@ -11,9 +11,31 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+int attention_tc_fault_take();
+int attention_bwd_tc_fault_take();
+int gemm_tc_fault_take();
+int gemm_wgrad_tc_fault_take();
 }  // namespace mvit
 
 extern "C" int mvit_abi_version(void) { return 1; }
+extern "C" int mvit_device_fault(void) {
+  int n = 0;
+  const char *names[4] = {"attention", "attention_bwd", "linear", "linear_wgrad"};
+  int (*take[4])() = {mvit::attention_tc_fault_take, mvit::attention_bwd_tc_fault_take, mvit::gemm_tc_fault_take,
+                      mvit::gemm_wgrad_tc_fault_take};
+  for (int i = 0; i < 4; ++i) {
+    const int v = take[i]();
+    if (v < 0) {
+      mvit::set_error("mvit_device_fault: reading the fault flag failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -2;
+    }
+    if (v > 0) {
+      mvit::set_error("a %s kernel abandoned an mbarrier wait (pipeline protocol fault): its results are invalid", names[i]);
+      ++n;
+    }
+  }
+  return n;
+}
 extern "C" const char *mvit_last_error(void) { return mvit::g_err; }
 extern "C" int mvit_device_supported(void) {
   int dev = 0;

@@ -570,12 +570,8 @@ int attention_bwd_tc(const AttnBwdArgs &a, cudaStream_t st) {
     const uint32_t box[4] = {kChunkCols, 1, (uint32_t)box_rows, 1};
     return encode_tmap_bf16(m, a.dout, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
   };
-  static bool attr_set = false;
-  if (!attr_set) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::kSmemBytes));
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::kSmemBytes));
-    attr_set = true;
-  }
+  MVIT_SMEM_OPT_IN(attention_bwd_dq_kernel, dq::kSmemBytes);
+  MVIT_SMEM_OPT_IN(attention_bwd_dkv_kernel, dkv::kSmemBytes);
   const float scale_log2 = a.scale * kLog2e;
   int r;
   {
@@ -609,5 +605,7 @@ int attention_bwd_tc(const AttnBwdArgs &a, cudaStream_t st) {
   }
   return 0;
 }
+
+int attention_bwd_tc_fault_take() { return tc_fault_take(); }
 
 }  // namespace mvit

@@ -377,6 +377,7 @@ bool attention_tc_supported(const AttnArgs &a, const char **why) {
   auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) { *why = "pointers must be 16-byte aligned"; return false; }
   if ((int64_t)a.B * a.heads >= 65536) { *why = "B*heads too large"; return false; }
+  if (a.Lq < 1 || a.Lk < 1 || a.B < 1 || a.heads < 1) { *why = "empty problem (Lq, Lk, B, heads must be >= 1)"; return false; }
   return true;
 }
 
@@ -399,15 +400,16 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
     const uint32_t box[4] = {attn::kChunkCols, 1, attn::BQ, 1};
     if ((r = encode_tmap_bf16(&to, a.out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
   }
-  static int poly = -1;
-  if (poly < 0) {
-    const char *e = getenv("MVIT_ATTN_POLY");      // tuning knob; default: a quarter of the exponentials on the FMA pipe
-    poly = e ? atoi(e) : 1;
-    if (poly < 0 || poly > 2) poly = 1;
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attn::attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
-  }
+  // tuning knob read once (a function-local static is initialised thread-safely); default: a quarter of the
+  // exponentials on the FMA pipe
+  static const int poly = [] {
+    const char *e = getenv("MVIT_ATTN_POLY");
+    const int v = e ? atoi(e) : 1;
+    return (v < 0 || v > 2) ? 1 : v;
+  }();
+  MVIT_SMEM_OPT_IN(attn::attention_tc_kernel<0>, attn::kSmemBytes);
+  MVIT_SMEM_OPT_IN(attn::attention_tc_kernel<1>, attn::kSmemBytes);
+  MVIT_SMEM_OPT_IN(attn::attention_tc_kernel<2>, attn::kSmemBytes);
   attn::Params p{static_cast<const bf16 *>(a.q), static_cast<bf16 *>(a.out), a.lse, a.heads, a.Lq, a.Lk, a.add_q,
                  a.scale * 1.44269504088896340736f};
   dim3 grid((unsigned)((a.Lq + 2 * attn::BQ - 1) / (2 * attn::BQ)), (unsigned)BH);
@@ -417,5 +419,7 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
   MVIT_LAUNCH_OK("attention(tcgen05)");
   return 0;
 }
+
+int attention_tc_fault_take() { return tc_fault_take(); }
 
 }  // namespace mvit

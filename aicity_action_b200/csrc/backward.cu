@@ -707,12 +707,8 @@ extern "C" int mvit_attention_bwd(const void *q, const void *k, const void *v, c
   }
   dim3 grid((Lq + ABQ - 1) / ABQ, B * heads);
   const size_t smem = sizeof(AttnBwdSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVIT_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  MVIT_SMEM_OPT_IN(attention_bwd_kernel<float>, smem);
+  MVIT_SMEM_OPT_IN(attention_bwd_kernel<bf16>, smem);
   if (dtype == MVIT_F32)
     attention_bwd_kernel<float><<<grid, 128, smem, st>>>(static_cast<const float *>(q), static_cast<const float *>(k), static_cast<const float *>(v), static_cast<const float *>(out), static_cast<const float *>(dout), lse, static_cast<float *>(dq), dk, dv, heads, Lq, Lk, scale, add_q_residual ? 1 : 0);
   else

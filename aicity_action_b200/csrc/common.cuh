@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/mvit_b200.h"
 
 namespace mvit {
@@ -111,15 +113,34 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return cdf + x * pdf;
 }
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs; racing first calls write
+// the same value).
 inline int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int> &slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when it is called: do it once
+// per (kernel, device), thread-safe (a bit per device in an atomic mask; a lost race only repeats an idempotent call).
+#define MVIT_SMEM_OPT_IN(kernel, bytes)                                                                          \
+  do {                                                                                                           \
+    static std::atomic<uint64_t> done__{0};                                                                      \
+    int dev__ = 0;                                                                                               \
+    cudaGetDevice(&dev__);                                                                                       \
+    const uint64_t bit__ = 1ull << (dev__ & 63);                                                                 \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                                                     \
+      MVIT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      done__.fetch_or(bit__, std::memory_order_release);                                                         \
+    }                                                                                                            \
+  } while (0)
 
 }  // namespace mvit

@@ -481,11 +481,7 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   } else {
     tr = ty;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
-  }
+  MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<BN, PAIR>), C::kSmemBytes);
   gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0, {}};
   constexpr int TM = PAIR ? 2 * gemm::BM : gemm::BM;
   const int64_t tiles = ((a.M + TM - 1) / TM) * ((a.N + BN - 1) / BN);
@@ -543,11 +539,7 @@ int patch_conv_tc(const void *folded, const void *wf, const float *bias, const v
       tr = ty;
     }
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(gemm::linear_tc_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
-  }
+  MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<96, false>), C::kSmemBytes);
   const int64_t M = (int64_t)B * Tf * Hf * Wf;
   gemm::Params p{bias, nullptr, M, 0, 0, N, K, MVIT_EPI_NONE, pos ? 1 : 0,
                  {1, Tf, Hf, Wf, Cf / gemm::BK, nt, nh, nw, lo_t, lo_h, lo_w}};
@@ -565,5 +557,7 @@ int linear_tc(const LinearArgs &a, cudaStream_t st) {
   if (a.K >= 384 && a.N % 128 == 0 && ((a.M + 127) / 128) * (a.N / 128) >= num_sms()) return launch_tc<128, false>(a, st);
   return launch_tc<96, false>(a, st);
 }
+
+int gemm_tc_fault_take() { return tc_fault_take(); }
 
 }  // namespace mvit

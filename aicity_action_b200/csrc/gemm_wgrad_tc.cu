@@ -163,11 +163,7 @@ static int launch_wgrad(const void *dy, const void *x, float *dw, float *db, int
   int r;
   if ((r = enc2(&tdy, dy, (uint64_t)N, (uint64_t)M))) return r;
   if ((r = enc2(&tx, x, (uint64_t)K, (uint64_t)M))) return r;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(wgrad::linear_wgrad_tc_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
-  }
+  MVIT_SMEM_OPT_IN(wgrad::linear_wgrad_tc_kernel<BQ>, C::kSmemBytes);
   const int p_tiles = (N + wgrad::BP - 1) / wgrad::BP, q_tiles = (K + BQ - 1) / BQ, tiles = p_tiles * q_tiles;
   const int64_t chunks = (M + wgrad::BMT - 1) / wgrad::BMT;
   int64_t splits = std::max<int64_t>(1, (2 * num_sms() + tiles - 1) / tiles);
@@ -184,5 +180,7 @@ static int launch_wgrad(const void *dy, const void *x, float *dw, float *db, int
 int linear_wgrad_tc(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, cudaStream_t st) {
   return K > 128 ? launch_wgrad<192>(dy, x, dw, db, M, N, K, st) : launch_wgrad<128>(dy, x, dw, db, M, N, K, st);
 }
+
+int gemm_wgrad_tc_fault_take() { return tc_fault_take(); }
 
 }  // namespace mvit

@@ -154,11 +154,7 @@ static int launch_wgrad(const void *in, const void *dy, float *dw, const PoolPar
   using G = Geo<S, kWgCPW>;
   const size_t smem = Ring<T>::kStages * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS_PAD * sizeof(int) +
                       96 * 27 * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(pool_wgrad_tiled_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  MVIT_SMEM_OPT_IN((pool_wgrad_tiled_kernel<T, S>), smem);
   const int tiles_h = (p.Ho + G::TH - 1) / G::TH, tiles_w = (p.Wo + TW - 1) / TW, tiles = tiles_h * tiles_w;
   const int bh = p.B * p.heads;
   const int target = 4 * num_sms();                    // CTAs wanted (2 resident per SM, two waves)

@@ -253,11 +253,7 @@ static int launch(const void *in, const float *w, const float *g, const float *b
   using G = Geo<S, CPW>;
   const size_t smem = Ring<T>::kStages * (size_t)G::NPOS * IO<T>::kPitch + (size_t)G::NPOS_PAD * sizeof(int) +
                       (96 * 27 + 192 + kWarps * CPW * kStgPitch) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVIT_CUDA_OK(cudaFuncSetAttribute(pool_tiled_kernel<T, S, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  MVIT_SMEM_OPT_IN((pool_tiled_kernel<T, S, CPW>), smem);
   const int tiles_h = (p.Ho + G::TH - 1) / G::TH, tiles_w = (p.Wo + TW - 1) / TW;
   const int bh = p.B * p.heads;
   // split the frame axis until the grid covers the GPU about twice (each split re-reads one halo frame)

@@ -52,14 +52,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+// Bounded wait.  A protocol bug (or a lost TMA completion) must neither hang the GPU nor poison the CUDA context the way a
+// trap does: after ~2^26 polls the waiter raises a per-translation-unit device flag and returns; every wait that is still
+// spinning sees the flag within 1024 polls and returns too, so the kernel drains (with garbage results) and the HOST
+// learns of it through mvit_device_fault() (api.cu), which the Python wrappers call at their synchronisation points.
+namespace {
+__device__ unsigned int g_tc_fault = 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (mbar_try_wait(addr, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(addr, parity)) {
-    if (++spins > (1u << 26)) __trap();   // ~seconds: turns a hang into a launch error
+    if ((++spins & 1023u) == 0) {
+      if (*reinterpret_cast<volatile unsigned int *>(&g_tc_fault) != 0) return;
+      if (spins > (1u << 26)) {
+        atomicExch(&g_tc_fault, 1u);
+        return;
+      }
+    }
   }
+}
+// Host side: read-and-clear this translation unit's flag (synchronises the device; not for the hot path).
+static inline int tc_fault_take() {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_tc_fault, sizeof(v)) != cudaSuccess) return -1;
+  if (v != 0) {
+    const unsigned int z = 0;
+    cudaMemcpyToSymbol(g_tc_fault, &z, sizeof(z));
+  }
+  return (int)v;
 }
 
 // ---------------------------------------------------------------- TMA

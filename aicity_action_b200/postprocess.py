@@ -72,3 +72,106 @@ def top_chunk_per_class(agg_scores: np.ndarray, thresholds: Sequence[float], by:
         key = (lambda ch: ch[3]) if by == "score" else (lambda ch: ch[2])
         out[c] = sorted(chunks, key=key, reverse=True)[0]
     return out
+
+
+# ----------------------------------------------------------------------------- 3-view merge + submission writer
+def localise_actions(preds_by_file, thresholds, views_by_vid, num_class: int = 18, agg_method: str = "avg",
+                     sort_single: str = "score", sort_multi: str = "length", use_num_chunk: int = 1,
+                     video_fps: float = 30.0, log=None):
+    """scripts/aicity_inf.py:36-126, the whole post-processing of one submission.
+
+    preds_by_file: {file_id: [(t0, t1, scores[num_class])]} — what the sliding-window runner pickles per video;
+    thresholds:    {action_id: threshold} in the order of the threshold file (it fixes the output order);
+    views_by_vid:  {vid: [file_id of view 1, 2, 3]} in the order of the video-id csv.
+    Per file and action: per-frame aggregation, threshold chunks, stable sort by mean score (or length), top-k, frames ->
+    seconds.  Per vid and action: the chunks of the three synchronised views concatenated in view order, stable sort by
+    LENGTH (default) or score, top-k, then Python `round()` (banker's) +1 / -1 second.
+    Returns [(vid, action_id, start_sec, end_sec)] in the reference's order."""
+    aggregate_func = np.mean if agg_method == "avg" else np.max
+    say = log if log is not None else (lambda msg: None)
+    action_chunks = {}
+    for file_id, pred in preds_by_file.items():
+        frames = aggregate_predictions(pred, aggregate_func, num_class)
+        per_action = {}
+        for action_id, thr in thresholds.items():
+            chunks = get_chunks(frames[:, action_id], thr)
+            if not chunks:
+                say("warning, %s %s got no action chunks" % (file_id, action_id))
+                continue
+            chunks.sort(key=(lambda c: c[2]) if sort_single == "length" else (lambda c: c[3]), reverse=True)
+            per_action[action_id] = [(s / video_fps, e / video_fps, n, m) for s, e, n, m, _ in chunks[:use_num_chunk]]
+        action_chunks[file_id] = per_action
+    outputs = []
+    for vid, files in views_by_vid.items():
+        for action_id in thresholds:
+            merged = [c for f in files for c in action_chunks[f].get(action_id, [])]
+            if not merged:
+                say("warning, %s %s has no action chunks" % (vid, action_id))
+                continue
+            merged.sort(key=(lambda c: c[2]) if sort_multi == "length" else (lambda c: c[3]), reverse=True)
+            for c in merged[:use_num_chunk]:
+                outputs.append((vid, action_id, round(c[0]) + 1.0, round(c[1]) - 1.0))
+    return outputs
+
+
+def write_submission(outputs, path: str) -> None:
+    """aicity_inf.py:128-130: one `vid action_id start end` line per segment, seconds with six decimals."""
+    with open(path, "w") as f:
+        for vid, action_id, start, end in outputs:
+            f.write("%s %s %.6f %.6f\n" % (vid, action_id, start, end))
+
+
+def read_thresholds(path: str) -> dict:
+    """aicity_inf.py:47-50: `action_id threshold` per line; insertion order is the output order."""
+    out = {}
+    with open(path) as f:
+        for line in f:
+            if line.strip():
+                a, t = line.strip().split()
+                out[int(a)] = float(t)
+    return out
+
+
+def read_video_ids(path: str) -> dict:
+    """aicity_inf.py:52-58: csv with a header line, then `vid,file1,file2,file3`."""
+    out = {}
+    with open(path) as f:
+        for line in f.readlines()[1:]:
+            if line.strip():
+                vid, f1, f2, f3 = line.strip().split(",")
+                out[vid] = [f1, f2, f3]
+    return out
+
+
+def main(argv=None) -> int:
+    """Same positional arguments and options as scripts/aicity_inf.py (argparse block at :15-34)."""
+    import argparse
+    import os
+    import pickle
+    ap = argparse.ArgumentParser(prog="python -m aicity_action_b200.postprocess")
+    ap.add_argument("pred_pickle_path")
+    ap.add_argument("thres_file")
+    ap.add_argument("vid_csv")
+    ap.add_argument("output_file")
+    ap.add_argument("--num_class", default=18, type=int)
+    ap.add_argument("--agg_method", default="avg", choices=["avg", "max"])
+    ap.add_argument("--chunk_sort_base_single_vid", default="score", choices=["score", "length"])
+    ap.add_argument("--chunk_sort_base_multi_vid", default="length", choices=["score", "length"])
+    ap.add_argument("--use_num_chunk", default=1, type=int)
+    a = ap.parse_args(argv)
+    views = read_video_ids(a.vid_csv)
+    preds = {}
+    for files in views.values():
+        for fid in files:
+            with open(os.path.join(a.pred_pickle_path, "%s.pkl" % fid), "rb") as f:
+                preds[fid] = pickle.load(f)
+    outputs = localise_actions(preds, read_thresholds(a.thres_file), views, a.num_class, a.agg_method,
+                               a.chunk_sort_base_single_vid, a.chunk_sort_base_multi_vid, a.use_num_chunk, log=print)
+    print("total pred %s" % len(outputs))
+    write_submission(outputs, a.output_file)
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

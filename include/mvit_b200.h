@@ -53,6 +53,11 @@ int mvit_abi_version(void);
 const char *mvit_last_error(void);
 /* 1 when the current device is sm_100 (B200); 0 otherwise; negative on CUDA error. */
 int mvit_device_supported(void);
+/* Number of tensor-core kernel families that abandoned an mbarrier wait since the last call (0 = healthy).  The
+ * kernels never trap (a trap would poison the CUDA context): a wait that exceeds ~2^26 polls raises a device flag,
+ * the kernel drains, and this call reads and clears the flags.  It SYNCHRONISES the device: call it where the host
+ * synchronises anyway (after a step / before trusting results), never inside a captured region. */
+int mvit_device_fault(void);
 
 /*
  * LayerNorm over the last dimension.   y[r,:] = (x[r,:]-mean)/sqrt(var+eps)*gamma+beta

@@ -119,3 +119,48 @@ def test_randomised_window_logic_matches_oracle():
         preds = [(t0, t1, rng.rand(18).astype(np.float32)) for t0, t1 in wl]
         assert np.array_equal(PP.aggregate_predictions(preds, np.mean, 18), WO.aggregate(preds, 18, "mean"))
         assert np.array_equal(PP.aggregate_predictions(preds, np.max, 18), WO.aggregate(preds, 18, "max"))
+
+
+# ----------------------------------------------------------------------------- 3-view merge + submission writer (N2)
+def _our_submission(tmp_path, extra=()):
+    from tests.golden.postprocess_case import write_inputs
+    pkl, thr, csv = write_inputs(str(tmp_path))
+    out = str(tmp_path / "ours.txt")
+    assert PP.main([pkl, thr, csv, out, *extra]) == 0
+    return open(out).read()
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VARIANT = ["--agg_method", "max", "--chunk_sort_base_single_vid", "length", "--chunk_sort_base_multi_vid", "score",
+           "--use_num_chunk", "2"]
+
+
+def test_submission_matches_reference_script_fixture(tmp_path):
+    """Byte-identical to what the unmodified scripts/aicity_inf.py wrote for the same pickles (fixture generated by
+    oracle/make_golden_postprocess.py): per-view chunks, 3-view merge by length, round()+-1, '%s %s %.6f %.6f'."""
+    assert _our_submission(tmp_path) == open(os.path.join(GOLDEN_DIR, "aicity_inf_expected.txt")).read()
+    assert _our_submission(tmp_path, VARIANT) == open(os.path.join(GOLDEN_DIR, "aicity_inf_expected_max_len_score_k2.txt")).read()
+
+
+def test_submission_matches_reference_script_live(tmp_path):
+    """The same comparison against the vendored reference script executed now (skipped when oracle/_ref is absent)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "oracle", "_ref", "scripts")):
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import make_golden_postprocess as G
+    G.ref_shims.REFERENCE_ROOT = os.path.join(root, "oracle", "_ref")
+    ref = G.run_reference(str(tmp_path / "ref"))
+    assert _our_submission(tmp_path / "ours") == ref
+
+
+def test_merge_prefers_longest_view_and_bankers_rounding():
+    mk = lambda a, b: [(16 * i, 16 * i + 64, np.where(np.arange(18) == 3, 0.9 if a <= i < b else 0.0, 0).astype(np.float32))
+                       for i in range(40)]
+    preds = {"v1": mk(2, 5), "v2": mk(10, 20), "v3": mk(30, 31)}
+    out = PP.localise_actions(preds, {3: 0.5, 4: 0.5}, {"7": ["v1", "v2", "v3"]})
+    assert len(out) == 1 and out[0][:2] == ("7", 3)
+    # view 2's chunk is the longest.  A frame in block k (16 frames) is covered by windows k-3..k; its mean is >= 0.5 when
+    # at least 3 of them lie in [10, 20): blocks 12..20 = frames [192, 336); the closing frame 336 belongs to the chunk
+    start, end = out[0][2], out[0][3]
+    assert (start, end) == (round(192 / 30.0) + 1.0, round(336 / 30.0) - 1.0) == (7.0, 10.0)
