@@ -40,6 +40,7 @@ SIGNATURES = {
     "mvit_fold_clip_fwd": (_i, [_p, _i, _p] + [_i] * 9 + [_f, _f, _p]),
     "mvit_patch_conv_fwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 12 + [_p]),
     "mvit_preprocess_u8_fwd": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _p]),
+    "mvit_resize_gather_u8": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p]),
     "mvit_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "mvit_gelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p]),
     "mvit_linear_wgrad": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),

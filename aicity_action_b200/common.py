@@ -11,8 +11,12 @@ def drop_path_scale(batch: int, drop_prob: float, training: bool, device, dtype=
     """Per-sample multiplier of stochastic depth (common.py:46-59): floor(keep + U[0,1)) / keep.
 
     Returns None when the path is kept deterministically (eval or p == 0).  The random draw uses
-    torch's generator exactly like the reference (`torch.rand(shape, dtype, device)`), so a seeded run
-    consumes the RNG stream identically; the multiply itself is fused into the GEMM epilogue."""
+    torch's generator like the reference (`torch.rand(shape, dtype, device)`).  MultiScaleBlock draws both masks of a
+    block up front in fp32 (attention branch, then MLP branch): with MVIT.DROPOUT_RATE == 0 (every shipped config) and
+    fp32 activations that is exactly the reference's consumption of the RNG stream; with dropout layers active or bf16
+    activations the reference interleaves its draws differently (dropout masks sit between the two DropPath draws, and
+    it draws in the activation dtype), so seeded runs are then statistically, not bitwise, equivalent.  The multiply
+    itself is fused into the GEMM epilogue."""
     if drop_prob == 0.0 or not training:
         return None
     keep = 1.0 - drop_prob

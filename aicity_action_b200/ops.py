@@ -286,6 +286,29 @@ def preprocess_u8(frames: torch.Tensor, dtype: torch.dtype, mean: float = 0.45, 
     return out
 
 
+def resize_gather_u8(frames: torch.Tensor, frame_idx: Optional[torch.Tensor], out_hw: Tuple[int, int],
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frames [n, H, W, C] uint8 (device) -> [len(frame_idx) or n, out_h, out_w, C] uint8: output frame i is source frame
+    frame_idx[i] resized exactly as `cv2.resize(frame, (out_w, out_h), interpolation=cv2.INTER_LINEAR)` does
+    (scripts/utils.py:207-211).  `frame_idx`: int32 device tensor or None (identity)."""
+    global launch_count
+    _need_cuda(frames, frame_idx, out)
+    assert frames.dtype == torch.uint8 and frames.ndim == 4 and frames.is_contiguous()
+    n, H, W, Cc = frames.shape
+    n_out = n if frame_idx is None else frame_idx.numel()
+    if frame_idx is not None:
+        assert frame_idx.dtype == torch.int32 and frame_idx.is_contiguous()
+    oh, ow = out_hw
+    if out is None:
+        out = torch.empty((n_out, oh, ow, Cc), dtype=torch.uint8, device=frames.device)
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == n_out * oh * ow * Cc
+    with _Timed("resize_u8", float(frames.numel() + out.numel())):
+        check(_lib.load().mvit_resize_gather_u8(_ptr(frames), n, H, W, _ptr(frame_idx), n_out, _ptr(out), oh, ow, Cc,
+                                                _stream()), "mvit_resize_gather_u8")
+    launch_count += 1
+    return out
+
+
 def im2col3d(clip: torch.Tensor, kernel: Sequence[int], stride: Sequence[int], padding: Sequence[int], Kp: int):
     """clip [B, C, T, H, W] -> patch matrix [B*To*Ho*Wo, Kp] (zero padded), see mvit_im2col3d_fwd."""
     global launch_count

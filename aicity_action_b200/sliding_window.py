@@ -58,11 +58,16 @@ class SyntheticVideo:
 
     PERIOD = 61      # distinct frames per video: frame f is texture f % PERIOD (enough that every window is unique)
 
-    def __init__(self, seed: int, num_frames: int, size: int, fps: float = 30.0):
+    def __init__(self, seed: int, num_frames: int, size: int, fps: float = 30.0, raw_hw=None):
+        """`raw_hw=(H, W)`: the video is held at its native resolution (e.g. (540, 960)) and resized to `size` per window
+        like the reference does — on the device by the runner (`get_raw_into`), or on the host with cv2 (`get_batch`)."""
         self.seed, self.num_frames, self.size, self.fps = seed, num_frames, size, fps
+        self.raw_hw = tuple(raw_hw) if raw_hw is not None else None
+        h, w = self.raw_hw if self.raw_hw is not None else (size, size)
         g = torch.Generator().manual_seed(seed)
-        self._base = torch.randint(0, 256, (size, size, 3), dtype=torch.uint8, generator=g)
-        self._ramp = torch.arange(size, dtype=torch.int32).view(size, 1, 1)
+        self._base = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g)
+        self._ramp = torch.arange(h, dtype=torch.int32).view(h, 1, 1)
+        self._hw = (h, w)
         self._pool = None
 
     def __len__(self):
@@ -70,7 +75,7 @@ class SyntheticVideo:
 
     def _texture(self, k: int) -> torch.Tensor:
         # cheap, deterministic: circular shift of a base texture plus a ramp
-        img = torch.roll(self._base, shifts=(k % self.size, (3 * k) % self.size), dims=(0, 1)).to(torch.int32)
+        img = torch.roll(self._base, shifts=(k % self._hw[0], (3 * k) % self._hw[1]), dims=(0, 1)).to(torch.int32)
         return ((img + (self._ramp * (k % 7))) % 256).to(torch.uint8)
 
     def frame(self, f: int) -> torch.Tensor:
@@ -79,7 +84,14 @@ class SyntheticVideo:
     def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
         """[T, S, S, 3] uint8: one gather from the (lazily built) texture pool, so that host-side frame synthesis does not
         bound the benchmark the way a Python loop over frames did."""
-        return self._textures()[torch.as_tensor([int(i) % self.PERIOD for i in idxs])]
+        raw = self._textures()[torch.as_tensor([int(i) % self.PERIOD for i in idxs])]
+        if self.raw_hw is None or self._hw == (self.size, self.size):
+            return raw
+        import cv2
+        out = np.empty((len(idxs), self.size, self.size, 3), dtype=np.uint8)
+        for n in range(len(idxs)):                       # the reference's host path (scripts/utils.py:207-211)
+            cv2.resize(raw[n].numpy(), (self.size, self.size), dst=out[n], interpolation=cv2.INTER_LINEAR)
+        return torch.from_numpy(out)
 
     def _textures(self) -> torch.Tensor:
         if self._pool is None:
@@ -89,6 +101,13 @@ class SyntheticVideo:
     def get_batch_into(self, idxs: Sequence[int], out: torch.Tensor) -> None:
         """Same frames as `get_batch`, written straight into `out` ([T, S, S, 3] uint8, e.g. a slice of a pinned staging
         buffer): one copy per frame instead of gather + stack + pin."""
+        if self.raw_hw is not None and self._hw != (self.size, self.size):
+            out.copy_(self.get_batch(idxs))
+            return
+        torch.index_select(self._textures(), 0, torch.as_tensor([int(i) % self.PERIOD for i in idxs]), out=out)
+
+    def get_raw_into(self, idxs: Sequence[int], out: torch.Tensor) -> None:
+        """Native-resolution frames into `out` [n, H, W, 3] (pinned staging); the runner resizes them on the device."""
         torch.index_select(self._textures(), 0, torch.as_tensor([int(i) % self.PERIOD for i in idxs]), out=out)
 
 
@@ -100,9 +119,16 @@ class ArrayVideo:
 
     def __init__(self, frames, size: int, fps: float = 30.0):
         self.frames, self.size, self.fps = frames, size, fps
+        self.raw_hw = (int(frames.shape[1]), int(frames.shape[2]))
 
     def __len__(self):
         return int(self.frames.shape[0])
+
+    def get_raw_into(self, idxs: Sequence[int], out: torch.Tensor) -> None:
+        """Decoded frames at native resolution into `out` [n, H, W, 3] (pinned staging): the device resizes them."""
+        dst = out.numpy()
+        for n, i in enumerate(idxs):
+            dst[n] = self.frames[int(i)]
 
     def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
         import cv2
@@ -137,7 +163,7 @@ class SlidingWindowRunner:
     def __init__(self, model: Callable, num_frames: int = 16, sampling_rate: int = 4, proposal_stride: int = 16,
                  batch_size: int = 8, dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
                  rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None,
-                 use_cuda_graph: bool = False, host_threads: int = 3, n_stage: int = 4):
+                 use_cuda_graph: bool = False, host_threads: int = 3, n_stage: int = 4, device_resize=None):
         self.model, self.T, self.rate = model, num_frames, sampling_rate
         self.length, self.stride = num_frames * sampling_rate, proposal_stride   # run_action...py:76
         self.batch_size, self.dtype, self.device = batch_size, dtype, device
@@ -147,7 +173,10 @@ class SlidingWindowRunner:
         self._dbuf = [None, None]
         self._copy_stream = None
         self.host_threads, self.n_stage = max(1, host_threads), max(2, n_stage)
-        self._stage, self._stage_free = None, None
+        self._stage, self._stage_free = [None], None
+        # None: resize on the device whenever the video offers raw frames whose size differs from the model's; True / False force
+        self.device_resize = device_resize
+        self.h2d_bytes = 0                    # bytes uploaded so far (frames + index lists), for the bench's accounting
         if preprocess is None and device is not None and dtype != torch.bfloat16:
             from . import ops
             preprocess = lambda u8: ops.preprocess_u8(u8, dtype)
@@ -186,19 +215,34 @@ class SlidingWindowRunner:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         copy = self._copy_stream
-        frame_shape = tuple(video.get_batch([0]).shape[1:])
-        shape = (self.batch_size, self.T) + frame_shape
+        # Raw-frame path (N1): a video that exposes its decoded frames at native resolution (`raw_hw`, `get_raw_into`) is
+        # resized ON THE DEVICE: every frame a batch needs travels once (duplicates removed), and mvit_resize_gather_u8
+        # gathers the windows' frames by index and applies OpenCV's uint8 INTER_LINEAR arithmetic bit for bit
+        # (scripts/utils.py:207-211) straight into the clip buffer.  Otherwise frames arrive at the model resolution.
+        raw_hw = getattr(video, "raw_hw", None)
+        size = int(getattr(video, "size", 0)) or int(video.get_batch([0]).shape[1])
+        dev_resize = (self.device_resize is not False and raw_hw is not None and hasattr(video, "get_raw_into")
+                      and (tuple(raw_hw) != (size, size) or self.device_resize is True))
+        shape = (self.batch_size, self.T, size, size, 3)
+        nf_max = self.batch_size * self.T
+        up_shape = (nf_max,) + tuple(raw_hw) + (3,) if dev_resize else shape
         # Device side: two upload buffers that live as long as the runner (the captured graphs read them by address, and a
         # buffer allocated mid-stream could be a block that kernels in flight on the compute stream still use).  Host side:
-        # a ring of pinned staging buffers that the worker threads fill in place (`get_batch_into`): no per-batch
-        # cudaHostAlloc, one memcpy per frame.
-        if self._dbuf[0] is None or tuple(self._dbuf[0].shape) != shape:
+        # a ring of pinned staging buffers that the worker threads fill in place: no per-batch cudaHostAlloc, one memcpy
+        # per frame.
+        if self._dbuf[0] is None or tuple(self._dbuf[0].shape) != shape or tuple(self._stage[0].shape) != up_shape:
             cur.synchronize()
-            self._dbuf = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
-            self._stage = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(self.n_stage)]
+            if self._dbuf[0] is None or tuple(self._dbuf[0].shape) != shape:
+                self._dbuf = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._graphed = [None, None]
+            self._stage = [torch.empty(up_shape, dtype=torch.uint8).pin_memory() for _ in range(self.n_stage)]
+            self._stage_idx = [torch.zeros((nf_max,), dtype=torch.int32).pin_memory() for _ in range(self.n_stage)]
             self._stage_free = [torch.cuda.Event() for _ in range(self.n_stage)]
-            self._graphed = [None, None]
+            self._draw = ([torch.empty(up_shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+                          if dev_resize else [None, None])
+            self._didx = [torch.zeros((nf_max,), dtype=torch.int32, device=self.device) for _ in range(2)]
         dbuf, stage, stage_free = self._dbuf, self._stage, self._stage_free
+        stage_idx, draw, didx = self._stage_idx, self._draw, self._didx
         if self.use_cuda_graph and chunks and len(chunks[0]) == self.batch_size:
             # capture BEFORE any worker thread exists: CUDA calls from other threads during a global-mode stream capture
             # (cudaHostAlloc, event queries) can invalidate it
@@ -211,9 +255,17 @@ class SlidingWindowRunner:
         into = getattr(video, "get_batch_into", None)
 
         def fill(j, ids):
-            """Worker thread: gather the frames of batch j into staging buffer j % n_stage once its last upload is done."""
+            """Worker thread: gather the frames of batch j into staging buffer j % n_stage once its last upload is done.
+            Returns (pinned frames view, number of clips, number of distinct raw frames or None)."""
             k = j % self.n_stage
             stage_free[k].synchronize()
+            if dev_resize:
+                flat = [f for w in ids for f in frame_indices(*windows[w], self.T, len(video))]
+                uniq = sorted(set(flat))
+                pos = {f: n for n, f in enumerate(uniq)}
+                video.get_raw_into(uniq, stage[k][:len(uniq)])
+                stage_idx[k][:len(flat)] = torch.tensor([pos[f] for f in flat], dtype=torch.int32)
+                return stage[k][:len(uniq)], len(ids), len(uniq)
             buf = stage[k][:len(ids)]
             for n, w in enumerate(ids):
                 idxs = frame_indices(*windows[w], self.T, len(video))
@@ -221,7 +273,7 @@ class SlidingWindowRunner:
                     into(idxs, buf[n])
                 else:
                     buf[n].copy_(torch.as_tensor(video.get_batch(idxs)))
-            return buf
+            return buf, len(ids), None
 
         workers = ThreadPoolExecutor(max_workers=self.host_threads)
         pending, todo = deque(), iter(enumerate(chunks))
@@ -240,18 +292,27 @@ class SlidingWindowRunner:
         for ev in freed:
             ev.record(cur)
         outs, i = [], 0
+        from . import ops
         while pending:
-            frames = pending.popleft().result()
-            full = frames.shape[0] == self.batch_size
-            slot = i % 2
+            frames, n_clips, n_uniq = pending.popleft().result()
+            full = n_clips == self.batch_size
+            slot, k = i % 2, i % self.n_stage
+            dev_frames = dbuf[slot][:n_clips]
             with torch.cuda.stream(copy):
                 copy.wait_event(freed[slot])
-                dev_frames = dbuf[slot][:frames.shape[0]]
-                dev_frames.copy_(frames, non_blocking=True)
+                if dev_resize:
+                    draw[slot][:n_uniq].copy_(frames, non_blocking=True)
+                    didx[slot][:n_clips * self.T].copy_(stage_idx[k][:n_clips * self.T], non_blocking=True)
+                else:
+                    dev_frames.copy_(frames, non_blocking=True)
                 ready[slot].record(copy)
-                stage_free[i % self.n_stage].record(copy)
+                stage_free[k].record(copy)
+            self.h2d_bytes += frames.numel() + (4 * n_clips * self.T if dev_resize else 0)
             submit_next()
             cur.wait_event(ready[slot])
+            if dev_resize:
+                ops.resize_gather_u8(draw[slot][:n_uniq], didx[slot][:n_clips * self.T], (size, size),
+                                     out=dev_frames.view(n_clips * self.T, size, size, 3))
             if self.use_cuda_graph and full:
                 # full batches replay a captured graph per upload buffer (uint8 frames in, normalisation fused into the
                 # patch embed); the ragged last batch takes the eager path

@@ -155,6 +155,18 @@ int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, int T, int 
                            float std, int dtype, void *stream);
 
 /*
+ * Frame gather + uint8 bilinear resize, bit-exact with OpenCV `cv2.resize(frame_u8, (out_w, out_h), INTER_LINEAR)`
+ * (the reference resizes every uint8 frame of a window before the cast to float: scripts/utils.py:207-211 through
+ * scripts/module_wrapper.py:304-331, keep_scale=False).  src: [n_src, H, W, channels] interleaved uint8 frames on the
+ * device; frame_idx: device int32[n_out], output frame i is made from source frame frame_idx[i] (NULL: identity,
+ * n_out == n_src) — this is the per-window frame-index gather of module_wrapper.py:384-397 done on the device;
+ * dst: [n_out, out_h, out_w, channels] uint8.  Fixed-point arithmetic of OpenCV's HResizeLinear / VResizeLinear
+ * (11-bit coefficients); see csrc/resize.cu.  channels: 3 or 1.
+ */
+int mvit_resize_gather_u8(const uint8_t *src, int n_src, int H, int W, const int32_t *frame_idx, int n_out,
+                          uint8_t *dst, int out_h, int out_w, int channels, void *stream);
+
+/*
  * Patch embedding as an implicit GEMM (stem_helper.py:308-338 Conv3d + video_model_builder.py:1206-1223 pos-embed).
  *  1. mvit_fold_clip_fwd: space-to-depth of the clip by the conv stride,
  *       folded[b, t/st, h/sh, w/sw, ((t%st*sh + h%sh)*sw + w%sw)*C + c] = x[b, c, t, h, w]      (bf16, zero padded to Cf)

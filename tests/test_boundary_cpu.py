@@ -180,3 +180,24 @@ def test_drop_path_scale_consumes_rng_like_the_reference():
     assert torch.equal(s, ref)
     assert drop_path_scale(B, 0.0, True, torch.device("cpu")) is None
     assert drop_path_scale(B, p, False, torch.device("cpu")) is None
+
+
+def test_weight_cache_refreshes_in_place_and_can_be_invalidated():
+    """version-counted updates refresh the cached bf16 operand IN PLACE (a captured graph reading it by address
+    stays valid); `.data` updates bypass the version counter and need invalidate_caches()."""
+    import torch
+    from aicity_action_b200.weights import cached_weight, cached_weight_t, invalidate_caches
+    lin = torch.nn.Linear(8, 4)
+    a = cached_weight(lin.weight, torch.bfloat16)
+    at = cached_weight_t(lin.weight, torch.bfloat16)
+    ptr, ptr_t = a.data_ptr(), at.data_ptr()
+    with torch.no_grad():
+        lin.weight.mul_(2)
+    b = cached_weight(lin.weight, torch.bfloat16)
+    assert b.data_ptr() == ptr and torch.equal(b, lin.weight.detach().bfloat16())
+    lin.weight.data.mul_(2)                                   # invisible to the version counter
+    assert not torch.equal(cached_weight(lin.weight, torch.bfloat16), lin.weight.detach().bfloat16())
+    assert invalidate_caches(lin) == 1
+    c, ct = cached_weight(lin.weight, torch.bfloat16), cached_weight_t(lin.weight, torch.bfloat16)
+    assert c.data_ptr() == ptr and torch.equal(c, lin.weight.detach().bfloat16())
+    assert ct.data_ptr() == ptr_t and torch.equal(ct, lin.weight.detach().bfloat16().t())
