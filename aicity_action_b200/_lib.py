@@ -46,6 +46,9 @@ SIGNATURES = {
     "mvit_linear_wgrad": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "mvit_attention_bwd_workspace_floats": (C.c_size_t, [_i, _i, _i]),
     "mvit_attention_bwd": (_i, [_p] * 10 + [_i] * 5 + [_f, _i, _i, _i, _p]),
+    "mvit_adamw_workspace_floats": (C.c_size_t, []),
+    "mvit_adamw_hyper_floats": (C.c_size_t, []),
+    "mvit_adamw_clip_step": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
     "mvit_attention_pool_bwd": (_i, [_i, _p, _i64, _i64, _i64, _p, _p, _p, _p] + [_i] * 13 + [_p]),
 }
 

@@ -18,7 +18,7 @@ import torch.utils.checkpoint
 from torch.nn.init import trunc_normal_
 
 from . import autograd as AG
-from . import ops
+from . import ops, weights
 from .attention import MultiScaleBlock, _compute_dtype
 
 
@@ -50,7 +50,7 @@ class PatchEmbed(nn.Module):
     def _gemm_weight(self, dtype):
         """Conv weight as a [Cout, Kp] GEMM operand (Kp = C*kt*kh*kw rounded up to 64, zero padded), cached."""
         w = self.proj.weight
-        key = (dtype, w._version, w.device, w.data_ptr())
+        key = (dtype, w._version, w.device, w.data_ptr(), weights.generation())
         slot = getattr(self, "_b200_w", None)
         if slot is None or slot[0] != key:
             k = w[0].numel()
@@ -73,7 +73,7 @@ class PatchEmbed(nn.Module):
     def _folded_weight(self):
         """Conv3d weight scattered into the folded layout: [Cout, taps_t*taps_h*taps_w*Cf] bf16 (cached)."""
         w = self.proj.weight
-        key = (w._version, w.device, w.data_ptr())
+        key = (w._version, w.device, w.data_ptr(), weights.generation())
         slot = getattr(self, "_b200_wf", None)
         if slot is None or slot[0] != key:
             k, s, p, lo, taps, creal, cf = self._fold_geometry()
@@ -350,7 +350,7 @@ class MViT(nn.Module):
     def _pos_tokens(self, dtype):
         """[N, C] separable positional-embedding table in the activation dtype (cached per parameter version)."""
         ps, pt = self.pos_embed_spatial, self.pos_embed_temporal
-        key = (dtype, ps._version, pt._version, ps.device, ps.data_ptr(), pt.data_ptr())
+        key = (dtype, ps._version, pt._version, ps.device, ps.data_ptr(), pt.data_ptr(), weights.generation())
         slot = getattr(self, "_b200_pos", None)
         if slot is None or slot[0] != key:
             T, H, W = self.patch_dims

@@ -13,24 +13,46 @@ import torch
 
 _ATTR = "_b200_wcache"
 _STALE = "_b200_wstale"
+_SHADOW = "_b200_shadow"
+_GENERATION = 0
 
 
-def _refresh(param, attr, key, make):
+def generation() -> int:
+    """Bumped by optimizers that update master weights without touching autograd's version counter (optim.FusedAdamW):
+    part of every cache key, so derived operands (transposed / folded weights, pos-embed tables) rebuild after a step."""
+    return _GENERATION
+
+
+def bump_generation() -> None:
+    global _GENERATION
+    _GENERATION += 1
+
+
+def register_shadow(param: torch.Tensor, view: torch.Tensor) -> None:
+    """`view` (bf16, same shape) is maintained by the fused optimizer kernel as the tensor-core operand of `param`:
+    `cached_weight(param, bf16)` returns it without any per-step cast."""
+    setattr(param, _SHADOW, [view, param._version])
+
+
+def mark_shadow_current(param: torch.Tensor) -> None:
+    slot = getattr(param, _SHADOW, None)
+    if slot is not None:
+        slot[1] = param._version
+
+
+def _refresh(param, attr, key, source):
+    """`source()` -> an (un-materialised) view of the master weights in the operand's layout."""
     slot = getattr(param, attr, None)
     stale = getattr(param, _STALE, 0)
     if slot is not None and slot[0] == key and not (stale and slot[2] != stale):
         return slot[1]
-    fresh = None
-    if slot is not None and slot[0][0] == key[0] and slot[0][2] == key[2]:
-        old = slot[1]
-        src = make()
-        if old.shape == src.shape:
-            old.copy_(src)                       # same storage: captured graphs that read it by address stay valid
-            fresh = old
-        else:
-            fresh = src
-    if fresh is None:
-        fresh = make()
+    dtype = key[0]
+    src = source()
+    if slot is not None and slot[0][0] == dtype and slot[0][2] == key[2] and slot[1].shape == src.shape:
+        fresh = slot[1]
+        fresh.copy_(src)                         # cast (+ transpose) in one kernel, same storage: captured graphs that read
+    else:                                        # the operand by address stay valid
+        fresh = src.to(dtype).contiguous()
     try:
         setattr(param, attr, (key, fresh, stale))
     except AttributeError:                       # plain tensors without __dict__ are converted every call
@@ -60,12 +82,18 @@ def cached_weight(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     `_version`), re-allocated, or moved to another device."""
     if param.dtype == dtype and param.is_contiguous():
         return param.detach()
-    key = (dtype, param._version, param.device, param.data_ptr())
-    return _refresh(param, _ATTR, key, lambda: param.detach().to(dtype).contiguous())
+    shadow = getattr(param, _SHADOW, None)
+    if shadow is not None and shadow[0].dtype == dtype and shadow[0].device == param.device:
+        if shadow[1] != param._version:          # updated through torch (load_state_dict, manual in-place op): re-sync
+            shadow[0].copy_(param.detach())
+            shadow[1] = param._version
+        return shadow[0]
+    key = (dtype, param._version, param.device, param.data_ptr(), _GENERATION)
+    return _refresh(param, _ATTR, key, lambda: param.detach())
 
 
 def cached_weight_t(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """`param` [N, K] as a contiguous [K, N] `dtype` tensor — the operand of the input-gradient GEMM
     dx = dy · W (a Linear whose weight is Wᵀ).  Cached like `cached_weight`."""
-    key = (dtype, param._version, param.device, param.data_ptr())
-    return _refresh(param, _ATTR + "_t", key, lambda: param.detach().to(dtype).t().contiguous())
+    key = (dtype, param._version, param.device, param.data_ptr(), _GENERATION)
+    return _refresh(param, _ATTR + "_t", key, lambda: param.detach().t())

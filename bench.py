@@ -204,7 +204,9 @@ def sliding_window_leg(model, cfg, dev, rank, world, B, n_frames, n_views, barri
     """BASELINE config 3: sliding-window temporal localisation over `n_views` synthetic views of `n_frames` frames (10 min at
     30 fps), windows dealt w % R to the ranks, ONE NCCL all_gather of the per-window scores per video (the path of
     scripts/run_action_classification_temporal_inf.py:91-130).  Frames are host uint8, already at the model resolution;
-    every batch is gathered on the host, uploaded and normalised on the device inside the timed region.  After the timed
+    Frames are host uint8 at the videos' native 540p: per batch every distinct frame is gathered into pinned staging
+    and uploaded once, then gathered per window, resized (OpenCV-exact uint8 INTER_LINEAR, scripts/utils.py:207-211) and
+    normalised on the device, all inside the timed region.  After the timed
     region rank 0 re-runs view 0 alone (world 1) and checks the gathered table against it bit for bit."""
     import numpy as np
     import torch
@@ -213,8 +215,10 @@ def sliding_window_leg(model, cfg, dev, rank, world, B, n_frames, n_views, barri
     size, nc, T = cfg.DATA.TRAIN_CROP_SIZE, cfg.MODEL.NUM_CLASSES, cfg.DATA.NUM_FRAMES
     kw = dict(num_frames=T, sampling_rate=cfg.DATA.SAMPLING_RATE, proposal_stride=16, batch_size=B, device=dev)
     runner = SlidingWindowRunner(model, rank=rank, world=world, use_cuda_graph=True, **kw)
-    runner.run_video(SyntheticVideo(99, 16 * B * world * 3, size), nc)     # graph capture + staging allocation, untimed
-    views = [SyntheticVideo(100 + v, n_frames, size) for v in range(n_views)]
+    raw_hw = (540, 960)                      # config 3: 540p views; resized to the model resolution on the device
+    runner.run_video(SyntheticVideo(99, 16 * B * world * 3, size, raw_hw=raw_hw), nc)   # graph capture + staging, untimed
+    runner.h2d_bytes = 0
+    views = [SyntheticVideo(100 + v, n_frames, size, raw_hw=raw_hw) for v in range(n_views)]
     for v in views:
         v._textures()                       # procedural frame synthesis stands for the decoder: outside the timed region
     barrier()
@@ -240,8 +244,9 @@ def sliding_window_leg(model, cfg, dev, rank, world, B, n_frames, n_views, barri
             "frames_per_view": n_frames, "seconds": float(t[0]), "wall_seconds": float(t[1]), "n_gpus": world,
             "sharding": "window w -> rank w % R; one all_gather of [ceil(n/R), 1+classes] fp32 per video"
                         + (" over NCCL" if world > 1 else " (single rank: no collective)"),
-            "h2d_bytes_per_window": T * size * size * 3,
-            "input": f"host uint8 frames [{T},{size},{size},3] per window, gathered per batch into pinned staging",
+            "h2d_bytes_per_window": runner.h2d_bytes * world / max(1, n_win),
+            "input": f"host uint8 frames at {raw_hw[0]}x{raw_hw[1]} (native), distinct frames of a batch uploaded once; "
+                     f"frame gather + cv2-exact resize to {size}x{size} + normalisation on the device",
             "sharded_equals_solo_view0": same,
             "identity_check": ("rank-0 solo graph-replay run of view 0 vs the gathered table, np.array_equal" if world > 1
                                else "eager launches vs graph replay on view 0, np.array_equal")}

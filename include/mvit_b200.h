@@ -155,6 +155,23 @@ int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, int T, int 
                            float std, int dtype, void *stream);
 
 /*
+ * Training-step glue (tools/train_net.py:229-246: zero_grad / clip_grad_norm_ / AdamW.step; slowfast/models/
+ * optimizer.py:200-206): fused AdamW + global-norm gradient clip over FLAT fp32 arenas laid out
+ * [decayed parameters (n_decay elements) | non-decayed], torch.optim.AdamW semantics (decoupled weight decay,
+ * bias-corrected moments).  Two launches: the squared-norm reduction (which also advances the step counter) and the
+ * update, which folds min(1, max_norm / (||g|| + 1e-6)) into the gradient and, when bf16_shadow != NULL, also writes the
+ * bf16 copy of every updated parameter (the tensor-core operand of the next forward).
+ * hyper: DEVICE float[mvit_adamw_hyper_floats()] = {lr, beta1, beta2, eps, weight_decay, max_norm (<= 0: no clip),
+ * int32 step (device-owned, start at 0), grad_norm (written: pre-clip norm of this step)} — read from memory at run
+ * time so that a captured CUDA graph of the step replays with a new learning rate.
+ * workspace: DEVICE float[mvit_adamw_workspace_floats()].  All arenas 16-byte aligned.
+ */
+size_t mvit_adamw_workspace_floats(void);
+size_t mvit_adamw_hyper_floats(void);
+int mvit_adamw_clip_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, void *bf16_shadow,
+                         int64_t n_decay, int64_t n, float *hyper, float *workspace, void *stream);
+
+/*
  * Frame gather + uint8 bilinear resize, bit-exact with OpenCV `cv2.resize(frame_u8, (out_w, out_h), INTER_LINEAR)`
  * (the reference resizes every uint8 frame of a window before the cast to float: scripts/utils.py:207-211 through
  * scripts/module_wrapper.py:304-331, keep_scale=False).  src: [n_src, H, W, channels] interleaved uint8 frames on the
