@@ -45,6 +45,12 @@ class _Timed:
         return False
 
 
+def device_fault_check():
+    """Raise if a tensor-core kernel abandoned an mbarrier wait since the last call (see mvit_device_fault).  Synchronises:
+    call it where the host synchronises anyway."""
+    _lib.device_fault_check()
+
+
 def _dt(t: torch.Tensor) -> int:
     try:
         return _DT[t.dtype]

@@ -188,29 +188,38 @@ class SlidingWindowRunner:
         length, stride = fps_adjusted_window(self.length, self.stride, getattr(video, "fps", 30.0))
         return window_list(len(video), length, stride)
 
-    @torch.no_grad()
     def local_scores(self, video, windows: List[Tuple[int, int]]) -> Tuple[List[int], torch.Tensor]:
-        """Scores of this rank's windows: (window ids, [n_local, classes] float32 on CPU).
+        """Scores of this rank's windows of one video: (window ids, [n_local, classes] float32 on CPU)."""
+        return self.local_scores_multi([video], [windows])[0]
 
-        On a device the batches are pipelined: host threads gather and pin the uint8 frames of the next batches while
-        batch i runs, uploads go through a copy stream into one of two device buffers, and the per-batch probabilities stay on
-        the device until the video is done (one synchronisation per video instead of one per batch)."""
-        mine = shard_windows(len(windows), self.rank, self.world)
-        chunks = [mine[b0:b0 + self.batch_size] for b0 in range(0, len(mine), self.batch_size)]
+    @torch.no_grad()
+    def local_scores_multi(self, videos, windows_list) -> List[Tuple[List[int], torch.Tensor]]:
+        """Scores of this rank's windows of several videos (e.g. the three synchronised views of one recording) as ONE
+        pipelined stream of batches: per video (window ids, [n_local, classes] float32 on CPU).
 
-        def host_batch(ids):
-            return torch.stack([video.get_batch(frame_indices(*windows[w], self.T, len(video))) for w in ids])
+        On a device the batches are pipelined: host threads gather the uint8 frames of the next batches into pinned staging
+        while batch i runs, uploads go through a copy stream into one of two device buffers, and the per-batch probabilities
+        stay on the device until every video is done (one synchronisation per call; the pipeline does not drain between
+        videos).  A ragged last batch of a video is padded by repeating its last window so that it, too, replays the captured
+        graph; the padded rows are dropped."""
+        mines = [shard_windows(len(w), self.rank, self.world) for w in windows_list]
+        jobs = [(v, mine[b0:b0 + self.batch_size]) for v, mine in enumerate(mines)
+                for b0 in range(0, len(mine), self.batch_size)]
 
         if self.device is None:                          # host-only logic (CPU tests with a stub model)
-            outs = []
-            for ids in chunks:
-                frames = host_batch(ids)
+            outs = [[] for _ in videos]
+            for v, ids in jobs:
+                video, windows = videos[v], windows_list[v]
+                frames = torch.stack([video.get_batch(frame_indices(*windows[w], self.T, len(video))) for w in ids])
                 clip = self.preprocess(frames) if self.preprocess is not None else frames
-                outs.append(self.model([clip]).float().cpu())
-            return mine, (torch.cat(outs) if outs else torch.zeros((0, 0)))
+                outs[v].append(self.model([clip]).float().cpu())
+            return [(mine, torch.cat(o) if o else torch.zeros((0, 0))) for mine, o in zip(mines, outs)]
+        if not jobs:
+            return [(mine, torch.zeros((0, 0))) for mine in mines]
 
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
+        from . import ops
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -219,9 +228,13 @@ class SlidingWindowRunner:
         # resized ON THE DEVICE: every frame a batch needs travels once (duplicates removed), and mvit_resize_gather_u8
         # gathers the windows' frames by index and applies OpenCV's uint8 INTER_LINEAR arithmetic bit for bit
         # (scripts/utils.py:207-211) straight into the clip buffer.  Otherwise frames arrive at the model resolution.
-        raw_hw = getattr(video, "raw_hw", None)
-        size = int(getattr(video, "size", 0)) or int(video.get_batch([0]).shape[1])
-        dev_resize = (self.device_resize is not False and raw_hw is not None and hasattr(video, "get_raw_into")
+        v0 = videos[0]
+        raw_hw = getattr(v0, "raw_hw", None)
+        size = int(getattr(v0, "size", 0)) or int(v0.get_batch([0]).shape[1])
+        for v in videos[1:]:
+            if getattr(v, "raw_hw", None) != raw_hw or (int(getattr(v, "size", 0)) or size) != size:
+                raise ValueError("local_scores_multi: the videos of one call must share resolution (run them one by one)")
+        dev_resize = (self.device_resize is not False and raw_hw is not None and hasattr(v0, "get_raw_into")
                       and (tuple(raw_hw) != (size, size) or self.device_resize is True))
         shape = (self.batch_size, self.T, size, size, 3)
         nf_max = self.batch_size * self.T
@@ -243,7 +256,7 @@ class SlidingWindowRunner:
             self._didx = [torch.zeros((nf_max,), dtype=torch.int32, device=self.device) for _ in range(2)]
         dbuf, stage, stage_free = self._dbuf, self._stage, self._stage_free
         stage_idx, draw, didx = self._stage_idx, self._draw, self._didx
-        if self.use_cuda_graph and chunks and len(chunks[0]) == self.batch_size:
+        if self.use_cuda_graph:
             # capture BEFORE any worker thread exists: CUDA calls from other threads during a global-mode stream capture
             # (cudaHostAlloc, event queries) can invalidate it
             from .graphed import GraphedForward
@@ -252,36 +265,41 @@ class SlidingWindowRunner:
                     pool = next((g.pool for g in self._graphed if g is not None), None)
                     dbuf[slot].zero_()
                     self._graphed[slot] = GraphedForward(self.model, dbuf[slot], pool=pool)
-        into = getattr(video, "get_batch_into", None)
+        pad = self.use_cuda_graph                        # ragged batches are padded to the captured batch size
 
-        def fill(j, ids):
-            """Worker thread: gather the frames of batch j into staging buffer j % n_stage once its last upload is done.
-            Returns (pinned frames view, number of clips, number of distinct raw frames or None)."""
+        def fill(j, v, ids):
+            """Worker thread: gather the frames of job j into staging buffer j % n_stage once its last upload is done.
+            Returns (pinned frames view, clips to run, clips to keep, number of distinct raw frames or None)."""
+            video, windows = videos[v], windows_list[v]
             k = j % self.n_stage
             stage_free[k].synchronize()
+            run_ids = ids + [ids[-1]] * (self.batch_size - len(ids)) if pad else ids
             if dev_resize:
-                flat = [f for w in ids for f in frame_indices(*windows[w], self.T, len(video))]
+                flat = [f for w in run_ids for f in frame_indices(*windows[w], self.T, len(video))]
                 uniq = sorted(set(flat))
                 pos = {f: n for n, f in enumerate(uniq)}
                 video.get_raw_into(uniq, stage[k][:len(uniq)])
                 stage_idx[k][:len(flat)] = torch.tensor([pos[f] for f in flat], dtype=torch.int32)
-                return stage[k][:len(uniq)], len(ids), len(uniq)
-            buf = stage[k][:len(ids)]
+                return stage[k][:len(uniq)], len(run_ids), len(ids), len(uniq)
+            buf = stage[k][:len(run_ids)]
+            into = getattr(video, "get_batch_into", None)
             for n, w in enumerate(ids):
                 idxs = frame_indices(*windows[w], self.T, len(video))
                 if into is not None:
                     into(idxs, buf[n])
                 else:
                     buf[n].copy_(torch.as_tensor(video.get_batch(idxs)))
-            return buf, len(ids), None
+            for n in range(len(ids), len(run_ids)):
+                buf[n].copy_(buf[len(ids) - 1])
+            return buf, len(run_ids), len(ids), None
 
         workers = ThreadPoolExecutor(max_workers=self.host_threads)
-        pending, todo = deque(), iter(enumerate(chunks))
+        pending, todo = deque(), iter(enumerate(jobs))
 
         def submit_next():
             nxt = next(todo, None)
             if nxt is not None:
-                pending.append(workers.submit(fill, *nxt))
+                pending.append(workers.submit(fill, nxt[0], *nxt[1]))
 
         for ev in stage_free:
             ev.record(cur)
@@ -291,11 +309,9 @@ class SlidingWindowRunner:
         freed = [torch.cuda.Event(), torch.cuda.Event()]
         for ev in freed:
             ev.record(cur)
-        outs, i = [], 0
-        from . import ops
+        outs, i = [[] for _ in videos], 0
         while pending:
-            frames, n_clips, n_uniq = pending.popleft().result()
-            full = n_clips == self.batch_size
+            frames, n_clips, n_keep, n_uniq = pending.popleft().result()
             slot, k = i % 2, i % self.n_stage
             dev_frames = dbuf[slot][:n_clips]
             with torch.cuda.stream(copy):
@@ -313,19 +329,19 @@ class SlidingWindowRunner:
             if dev_resize:
                 ops.resize_gather_u8(draw[slot][:n_uniq], didx[slot][:n_clips * self.T], (size, size),
                                      out=dev_frames.view(n_clips * self.T, size, size, 3))
-            if self.use_cuda_graph and full:
-                # full batches replay a captured graph per upload buffer (uint8 frames in, normalisation fused into the
-                # patch embed); the ragged last batch takes the eager path
-                probs = self._graphed[slot]().clone()
+            if self.use_cuda_graph and n_clips == self.batch_size:
+                # a captured graph per upload buffer (uint8 frames in, normalisation fused into the patch embed)
+                probs = self._graphed[slot]()[:n_keep].clone()
             else:
                 clip = self.preprocess(dev_frames) if self.preprocess is not None else dev_frames
-                probs = self.model([clip])
+                probs = self.model([clip])[:n_keep]
             freed[slot].record(cur)
-            outs.append(probs.float())
+            outs[jobs[i][0]].append(probs.float())
             i += 1
         workers.shutdown(wait=True)
-        scores = torch.cat(outs).cpu() if outs else torch.zeros((0, 0))
-        return mine, scores
+        host = [torch.cat(o).cpu() if o else torch.zeros((0, 0)) for o in outs]    # the one synchronisation of the call
+        ops.device_fault_check()
+        return list(zip(mines, host))
 
     def gather(self, n_windows: int, mine: List[int], scores: torch.Tensor, num_classes: int) -> Optional[torch.Tensor]:
         """One all_gather per video of a padded [ceil(n/R), 1 + classes] block (window id, scores); returns the
@@ -357,6 +373,19 @@ class SlidingWindowRunner:
         preds = [(int(t0), int(t1), table[w].numpy()) for w, (t0, t1) in enumerate(windows)]
         preds.sort(key=lambda x: x[0])
         return preds
+
+    def run_videos(self, videos, num_classes: int) -> List[List[Tuple[int, int, np.ndarray]]]:
+        """`run_video` for several videos of the same resolution (the 3 views of a recording): their batches form one
+        pipelined stream, then ONE all_gather per video exchanges the scores."""
+        windows_list = [self.windows_for(v) for v in videos]
+        local = self.local_scores_multi(videos, windows_list)
+        results = []
+        for windows, (mine, scores) in zip(windows_list, local):
+            table = self.gather(len(windows), mine, scores, num_classes)
+            preds = [(int(t0), int(t1), table[w].numpy()) for w, (t0, t1) in enumerate(windows)]
+            preds.sort(key=lambda x: x[0])
+            results.append(preds)
+        return results
 
     def run_and_save(self, video, video_name: str, out_dir: str, num_classes: int):
         preds = self.run_video(video, num_classes)

