@@ -217,6 +217,26 @@ class MultiScaleAttention(nn.Module):
             params += [w, getattr(norm, "weight", None), getattr(norm, "bias", None)]
         return tuple(descs), params
 
+    def _fused_pool_args(self, qkv):
+        """(weights, lns, strides) for ops.attention_pool_qkv when all three pools are the shipped 3x3x3 depthwise convs with
+        LayerNorm, no cls token, head_dim 96, bf16 — else None (generic per-tensor path)."""
+        if self.has_cls_embed or self.dim_out // self.num_heads != 96:
+            return None
+        ws, lns, strides = [], [], []
+        for pool, norm in ((self.pool_q, getattr(self, "norm_q", None)), (self.pool_k, getattr(self, "norm_k", None)),
+                           (self.pool_v, getattr(self, "norm_v", None))):
+            if pool is None or norm is None:
+                return None
+            mode, k, s, w = _pool_desc(pool)
+            if mode != "conv" or list(k) != [3, 3, 3]:
+                return None
+            ws.append(w)
+            lns.append((norm.weight, norm.bias, norm.eps))
+            strides.append(tuple(s))
+        if len({ln[2] for ln in lns}) != 1 or not ops.pool_qkv_supported(qkv, self.num_heads, strides):
+            return None
+        return ws, lns, strides
+
     def attend(self, x, thw_shape):
         """Everything before `proj`: returns (y [B, Lq, C], out_thw) with y = softmax(qkᵀ·scale)v (+q)."""
         B, N, _ = x.shape
@@ -245,6 +265,12 @@ class MultiScaleAttention(nn.Module):
                     out_shape = shp
                 parts.append(t.contiguous())
             return AG.attention(parts[0], parts[1], parts[2], self.scale, self.use_query_residual_pool), out_shape
+        fused = self._fused_pool_args(qkv)
+        if fused is not None:
+            # q, k and v pooled (+ LayerNorm) by one call that reads the qkv GEMM output in place: persistent TMA-fed kernel,
+            # tensors of equal stride share a launch
+            (q, k, v), grids, _ = ops.attention_pool_qkv(qkv, h, list(thw_shape), *fused)
+            return ops.attention(q, k, v, self.scale, self.use_query_residual_pool), grids[0]
         qkv5 = qkv.view(B, N, 3, h, C // h)
         # the three pooling launches are independent: K and V run on side streams next to Q so the small
         # deep-stage launches overlap instead of queueing (fork / join with events, graph-capturable)

@@ -178,6 +178,48 @@ def attention_pool_heads(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[i
     return out, out_thw
 
 
+def pool_qkv_supported(qkv: torch.Tensor, heads: int, strides) -> bool:
+    """Whether mvit_attention_pool_qkv_fwd applies: bf16 contiguous qkv GEMM output, head_dim 96, 3x3x3 conv pools of
+    stride (1, s, s) with s in {1, 2, 4, 8} on all three tensors (every block of the shipped FULL configurations)."""
+    return (qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape[-1] == 3 * heads * 96
+            and qkv.data_ptr() % 16 == 0 and all(s is not None and s[0] == 1 and s[1] == s[2] and s[1] in (1, 2, 4, 8)
+                                                 for s in strides))
+
+
+def attention_pool_qkv(qkv: torch.Tensor, heads: int, thw: Sequence[int], weights, lns, strides, save_pre: bool = False):
+    """qkv: [B, N, 3*heads*96] bf16 (the qkv GEMM output, read in place); weights[i]: [96,1,3,3,3] conv filters of q / k / v;
+    lns[i]: (gamma, beta) or None; strides[i]: (1, s, s).  One C-ABI call; returns ([q, k, v] pooled + LayerNorm-ed, contiguous
+    [B, heads, L', 96]), their [T, H', W'] grids, and (save_pre) the pre-LayerNorm conv outputs."""
+    global launch_count
+    import ctypes as C
+    _need_cuda(qkv, *weights)
+    B, N, _ = qkv.shape
+    T, H, W = thw
+    assert N == T * H * W
+    outs, pres, grids, keep = [], [], [], []
+    for s in strides:
+        g = pooled_thw(thw, [3, 3, 3], s)
+        grids.append(g)
+        outs.append(torch.empty((B, heads, g[0] * g[1] * g[2], 96), dtype=qkv.dtype, device=qkv.device))
+        pres.append(torch.empty_like(outs[-1]) if save_pre else None)
+    w32 = [_f32c(w).reshape(96, 27) for w in weights]
+    gam = [_f32c(ln[0]) if ln is not None else None for ln in lns]
+    bet = [_f32c(ln[1]) if ln is not None else None for ln in lns]
+    keep += w32 + gam + bet
+    arr = lambda ts: (C.c_void_p * 3)(*[_ptr(t) for t in ts])
+    sarr = (C.c_int * 3)(*[int(s[1]) for s in strides])
+    eps = next((float(ln[2]) for ln in lns if ln is not None), 0.0)
+    n_tma = len({int(s[1]) for s in strides if s[1] <= 2})
+    n_old = sum(1 for s in strides if s[1] > 2)
+    work = float(qkv.numel() + sum(o.numel() for o in outs) * (2 if save_pre else 1)) * qkv.element_size()
+    with _Timed("pool_conv", work):
+        check(_lib.load().mvit_attention_pool_qkv_fwd(_ptr(qkv), B, heads, T, H, W, arr(w32), arr(gam), arr(bet), sarr,
+                                                      arr(outs), arr(pres) if save_pre else None, eps, _dt(qkv), _stream()),
+              "mvit_attention_pool_qkv_fwd")
+    launch_count += n_tma + n_old
+    return outs, grids, pres
+
+
 def pool_save_supported(x: torch.Tensor, kernel: Sequence[int], stride: Sequence[int]) -> bool:
     """Whether mvit_attention_pool_fwd_save applies to this q/k/v view (the tuned kernel's conditions)."""
     es = x.element_size()

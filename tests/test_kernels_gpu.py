@@ -78,6 +78,43 @@ def test_attention_pool_reads_qkv_layout_in_place(dtype):
         assert rel_inf(got, ref) < TOL[dtype]
 
 
+@pytest.mark.parametrize("save", [False, True], ids=["infer", "save_pre"])
+@pytest.mark.parametrize("B,h,thw,strides", [
+    (2, 2, (4, 8, 8), (1, 2, 2)),            # q stride 1, k/v stride 2 (blocks 4-13): two TMA launches
+    (1, 3, (3, 7, 5), (1, 1, 1)),            # all stride 1 (block 15), odd grid: ragged tiles, one launch for q, k and v
+    (2, 1, (2, 16, 16), (1, 8, 8)),          # block 0: q on the TMA kernel, k/v (stride 8) on the tiled kernel
+    (1, 2, (4, 16, 16), (2, 4, 4)),          # block 1
+    (2, 4, (8, 12, 10), (2, 2, 2)),          # block 3: all stride 2, one launch
+    (1, 2, (9, 9, 17), (2, 1, 1)),           # block 14, T not a multiple of 3, odd sizes
+    (3, 2, (1, 4, 4), (1, 1, 1)),            # a single frame
+], ids=str)
+def test_attention_pool_qkv_fused(B, h, thw, strides, save):
+    """mvit_attention_pool_qkv_fwd (persistent TMA-fed kernel; q/k/v of one block in one call) against the oracle's
+    attention_pool on each of q, k, v: conv + LayerNorm(1e-5), and the saved pre-LayerNorm conv output."""
+    d = 96
+    N = math.prod(thw)
+    qkv = rounded(synth_input(9, f"qkv{B}{h}{thw}", (B, N, 3, h, d)), torch.bfloat16)
+    ws = [synth_tensor(9, f"pool_{n}.weight", (d, 1, 3, 3, 3)) for n in "qkv"]
+    lns = [(synth_tensor(9, f"norm_{n}.weight", (d,)), synth_tensor(9, f"norm_{n}.bias", (d,)), 1e-5) for n in "qkv"]
+    st = [(1, strides[0], strides[0]), (1, strides[1], strides[1]), (1, strides[2], strides[2])]
+    qd = dev(qkv, torch.bfloat16).reshape(B, N, 3 * h * d)
+    assert ops.pool_qkv_supported(qd, h, st)
+    outs, grids, pres = ops.attention_pool_qkv(qd, h, list(thw), [dev(w) for w in ws],
+                                               [(dev(g), dev(b), e) for g, b, e in lns], st, save_pre=save)
+    for i in range(3):
+        view = qkv[:, :, i].permute(0, 2, 1, 3)
+        ref, rthw = O.attention_pool(view, thw, mode="conv", kernel=[3, 3, 3], stride=list(st[i]), weight=ws[i], ln=lns[i])
+        assert grids[i] == rthw
+        assert rel_inf(outs[i], ref) < TOL[torch.bfloat16], (i, rel_inf(outs[i], ref))
+        if save:
+            pre, _ = O.attention_pool(view, thw, mode="conv", kernel=[3, 3, 3], stride=list(st[i]), weight=ws[i], ln=None)
+            assert rel_inf(pres[i], pre) < TOL[torch.bfloat16]
+        # and against the per-tensor kernel it replaces (same fp32 convolution order; the LayerNorm sums differ in order)
+        old, _ = ops.attention_pool_heads(qd.view(B, N, 3, h, d)[:, :, i].permute(0, 2, 1, 3), list(thw), [3, 3, 3],
+                                          list(st[i]), mode="conv", weight=dev(ws[i]), ln=(dev(lns[i][0]), dev(lns[i][1]), 1e-5))
+        assert rel_inf(outs[i], old) < 8e-3, i
+
+
 def _impls(dtype):
     return [IMPL_SIMT] if dtype == torch.float32 else [IMPL_SIMT, IMPL_AUTO]
 

@@ -112,6 +112,15 @@ def main():
                 ms = timeit(lambda: ops.attention_pool_heads(view, s["thw"], [3, 3, 3], st, mode="conv", weight=w,
                                                              ln=(g, b, 1e-5)), args.iters)
                 rec("pool", f"{tag} {'q' if which == 0 else 'k/v'} s={st}", ms, work, "hbm")
+            # the block's three pools in one call (mvit_attention_pool_qkv_fwd): all of qkv read + q, k, v written
+            q2 = qkv.view(B, N, 3 * h * 96)
+            st3 = [tuple(s["sq"]), tuple(s["skv"]), tuple(s["skv"])]
+            if ops.pool_qkv_supported(q2, h, st3):
+                w5 = w.view(96, 1, 3, 3, 3)
+                lo = [math.prod(ops.pooled_thw(s["thw"], [3, 3, 3], list(x))) for x in st3]
+                work = (3 * B * h * N * 96 + B * h * sum(lo) * 96) * 2.0
+                ms = timeit(lambda: ops.attention_pool_qkv(q2, h, list(s["thw"]), [w5] * 3, [(g, b, 1e-5)] * 3, st3), args.iters)
+                rec("pool_qkv", f"{tag} q+k+v s_q={s['sq'][1]} s_kv={s['skv'][1]}", ms, work, "hbm")
             del qkv
         if "attn" in what:
             Lq = math.prod(ops.pooled_thw(s["thw"], [3, 3, 3], s["sq"]))

@@ -41,6 +41,14 @@ elif what in ("pool_q", "pool_kv"):
     which, st = (0, [1, 1, 1]) if what == "pool_q" else (1, [1, 8, 8])
     view = qkv[:, :, which].permute(0, 2, 1, 3)
     fn = lambda: ops.attention_pool_heads(view, [8, 112, 112], [3, 3, 3], st, mode="conv", weight=w, ln=(g, bb, 1e-5))
+elif what in ("pool_qkv0", "pool_qkv4"):       # the fused q+k+v call at the block-0 / block-4 shapes
+    thw, h, sq, skv = ([8, 112, 112], 1, 1, 8) if what == "pool_qkv0" else ([8, 28, 28], 4, 1, 2)
+    N = thw[0] * thw[1] * thw[2]
+    qkv = torch.randn(B, N, 3 * h * 96, device="cuda", dtype=dt)
+    w = torch.randn(96, 1, 3, 3, 3, device="cuda")
+    g, bb = torch.ones(96, device="cuda"), torch.zeros(96, device="cuda")
+    st3 = [(1, sq, sq), (1, skv, skv), (1, skv, skv)]
+    fn = lambda: ops.attention_pool_qkv(qkv, h, thw, [w] * 3, [(g, bb, 1e-5)] * 3, st3)
 elif what == "ln":
     x = torch.randn(802816, 96, device="cuda", dtype=dt)
     g, bb = torch.ones(96, device="cuda"), torch.zeros(96, device="cuda")
