@@ -269,7 +269,22 @@ class MultiScaleAttention(nn.Module):
         if fused is not None:
             # q, k and v pooled (+ LayerNorm) by one call that reads the qkv GEMM output in place: persistent TMA-fed kernel,
             # tensors of equal stride share a launch
-            (q, k, v), grids, _ = ops.attention_pool_qkv(qkv, h, list(thw_shape), *fused)
+            ws, lns, strides = fused
+            if strides[0] == strides[1]:
+                (q, k, v), grids, _ = ops.attention_pool_qkv(qkv, h, list(thw_shape), ws, lns, strides)
+            else:
+                # two persistent launches (q; k + v): the second runs on a side stream so that its CTAs fill the SMs the first
+                # one's last wave leaves idle (fork / join with events, graph-capturable)
+                cur = torch.cuda.current_stream()
+                side = _side_streams(x.device)[0]
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    (_, k, v), _, _ = ops.attention_pool_qkv(qkv, h, list(thw_shape), ws, lns, strides, only=(1, 2))
+                    k.record_stream(cur)
+                    v.record_stream(cur)
+                (q, _, _), grids, _ = ops.attention_pool_qkv(qkv, h, list(thw_shape), ws, lns, strides, only=(0,))
+                cur.wait_stream(side)
+                qkv.record_stream(side)
             return ops.attention(q, k, v, self.scale, self.use_query_residual_pool), grids[0]
         qkv5 = qkv.view(B, N, 3, h, C // h)
         # the three pooling launches are independent: K and V run on side streams next to Q so the small

@@ -137,6 +137,18 @@ class _PoolQKV(Function):
         d = C3 // (3 * heads)
         qkv5 = qkv.view(B, N, 3, heads, d)
         outs, shapes, pres = [], [], [None, None, None]
+        strides3 = [tuple(dsc[1]) if dsc is not None else None for dsc in descs]
+        if (d == 96 and all(dsc is not None and tuple(dsc[0]) == (3, 3, 3) and dsc[2] is not None for dsc in descs)
+                and len({dsc[2] for dsc in descs}) == 1 and all(params[3 * i + 1] is not None for i in range(3))
+                and ops.pool_qkv_supported(qkv, heads, strides3)):
+            # the shipped configuration: one call pools q, k and v (persistent TMA kernel) and keeps their pre-LayerNorm values
+            outs, shapes, pres = ops.attention_pool_qkv(qkv, heads, list(thw), [params[0], params[3], params[6]],
+                                                        [(params[3 * i + 1], params[3 * i + 2], descs[i][2]) for i in range(3)],
+                                                        strides3, save_pre=True)
+            ctx.save_for_backward(qkv, *params, *pres)
+            ctx.meta = (heads, list(thw), descs)
+            ctx.out_tokens = [sh[0] * sh[1] * sh[2] for sh in shapes]
+            return tuple(outs)
         for i in range(3):
             t = qkv5[:, :, i].permute(0, 2, 1, 3)
             w, g, b = params[3 * i:3 * i + 3]

@@ -381,13 +381,14 @@ extern "C" int mvit_attention_pool_qkv_fwd(const void *qkv, int B, int heads, in
   MVIT_REQUIRE((int64_t)B * heads < 65536, "attention_pool_qkv: B*heads too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int i = 0; i < 3; ++i) {
+    if (strides_hw[i] == 0) continue;                       // tensor not pooled by this call
     MVIT_REQUIRE(weights[i] && outs[i], "attention_pool_qkv: tensor %d needs a weight and an output", i);
     MVIT_REQUIRE((gammas[i] == nullptr) == (betas[i] == nullptr), "attention_pool_qkv: gamma/beta must both be set or NULL");
     const int s = strides_hw[i];
     MVIT_REQUIRE(s == 1 || s == 2 || s == 4 || s == 8, "attention_pool_qkv: stride (1,%d,%d) unsupported", s, s);
     MVIT_REQUIRE((reinterpret_cast<uintptr_t>(outs[i]) & 15) == 0, "attention_pool_qkv: outputs must be 16-byte aligned");
   }
-  bool done[3] = {false, false, false};
+  bool done[3] = {strides_hw[0] == 0, strides_hw[1] == 0, strides_hw[2] == 0};
   for (int i = 0; i < 3; ++i) {
     if (done[i]) continue;
     const int s = strides_hw[i];

@@ -186,10 +186,12 @@ def pool_qkv_supported(qkv: torch.Tensor, heads: int, strides) -> bool:
                                                  for s in strides))
 
 
-def attention_pool_qkv(qkv: torch.Tensor, heads: int, thw: Sequence[int], weights, lns, strides, save_pre: bool = False):
+def attention_pool_qkv(qkv: torch.Tensor, heads: int, thw: Sequence[int], weights, lns, strides, save_pre: bool = False,
+                       only: Optional[Sequence[int]] = None):
     """qkv: [B, N, 3*heads*96] bf16 (the qkv GEMM output, read in place); weights[i]: [96,1,3,3,3] conv filters of q / k / v;
     lns[i]: (gamma, beta) or None; strides[i]: (1, s, s).  One C-ABI call; returns ([q, k, v] pooled + LayerNorm-ed, contiguous
-    [B, heads, L', 96]), their [T, H', W'] grids, and (save_pre) the pre-LayerNorm conv outputs."""
+    [B, heads, L', 96]), their [T, H', W'] grids, and (save_pre) the pre-LayerNorm conv outputs.  `only`: indices of the
+    tensors to pool in this call (the others come back as None) — lets a caller put q and k/v on different streams."""
     global launch_count
     import ctypes as C
     _need_cuda(qkv, *weights)
@@ -197,21 +199,23 @@ def attention_pool_qkv(qkv: torch.Tensor, heads: int, thw: Sequence[int], weight
     T, H, W = thw
     assert N == T * H * W
     outs, pres, grids, keep = [], [], [], []
-    for s in strides:
+    sel = set(range(3)) if only is None else set(only)
+    for i, s in enumerate(strides):
         g = pooled_thw(thw, [3, 3, 3], s)
         grids.append(g)
-        outs.append(torch.empty((B, heads, g[0] * g[1] * g[2], 96), dtype=qkv.dtype, device=qkv.device))
-        pres.append(torch.empty_like(outs[-1]) if save_pre else None)
+        outs.append(torch.empty((B, heads, g[0] * g[1] * g[2], 96), dtype=qkv.dtype, device=qkv.device) if i in sel else None)
+        pres.append(torch.empty_like(outs[-1]) if (save_pre and i in sel) else None)
     w32 = [_f32c(w).reshape(96, 27) for w in weights]
     gam = [_f32c(ln[0]) if ln is not None else None for ln in lns]
     bet = [_f32c(ln[1]) if ln is not None else None for ln in lns]
     keep += w32 + gam + bet
     arr = lambda ts: (C.c_void_p * 3)(*[_ptr(t) for t in ts])
-    sarr = (C.c_int * 3)(*[int(s[1]) for s in strides])
+    sarr = (C.c_int * 3)(*[int(s[1]) if i in sel else 0 for i, s in enumerate(strides)])
     eps = next((float(ln[2]) for ln in lns if ln is not None), 0.0)
-    n_tma = len({int(s[1]) for s in strides if s[1] <= 2})
-    n_old = sum(1 for s in strides if s[1] > 2)
-    work = float(qkv.numel() + sum(o.numel() for o in outs) * (2 if save_pre else 1)) * qkv.element_size()
+    n_tma = len({int(s[1]) for i, s in enumerate(strides) if s[1] <= 2 and i in sel})
+    n_old = sum(1 for i, s in enumerate(strides) if s[1] > 2 and i in sel)
+    work = float(qkv.numel() // 3 * len(sel) + sum(o.numel() for o in outs if o is not None) * (2 if save_pre else 1)) \
+        * qkv.element_size()
     with _Timed("pool_conv", work):
         check(_lib.load().mvit_attention_pool_qkv_fwd(_ptr(qkv), B, heads, T, H, W, arr(w32), arr(gam), arr(bet), sarr,
                                                       arr(outs), arr(pres) if save_pre else None, eps, _dt(qkv), _stream()),

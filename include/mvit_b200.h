@@ -158,7 +158,8 @@ int mvit_preprocess_u8_fwd(const uint8_t *frames, void *clip, int B, int T, int 
  * The three conv poolings of one attention block in one call (attention.py:172-212 pool_q / pool_k / pool_v + their
  * LayerNorms), reading the fused qkv GEMM output IN PLACE: qkv is [B, T*H*W, 3, heads, 96] bf16 contiguous.
  * weights[i] / gammas[i] / betas[i] (i = 0 q, 1 k, 2 v): fp32 [96, 27] depthwise 3x3x3 filter, LayerNorm scale / shift
- * (both NULL: no LayerNorm).  strides_hw[i] = s for stride (1, s, s), s in {1, 2, 4, 8}; padding 1.
+ * (both NULL: no LayerNorm).  strides_hw[i] = s for stride (1, s, s), s in {1, 2, 4, 8}; padding 1; s = 0 skips tensor i
+ * (a caller may pool q on one stream and k, v on another).
  * outs[i]: [B, heads, T*H'*W', 96] bf16 contiguous, H' = (H - 1) / s + 1.  pre_outs (may be NULL, or hold NULL entries):
  * the conv output before the LayerNorm, same layout (saved for the LayerNorm backward in training).
  * Tensors of stride 1 / 2 run on a persistent TMA-fed kernel (equal strides share one launch); strides 4 / 8 on the
