@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from . import autograd as AG
 from . import ops
+from . import weights
 from .common import DropPath, Mlp, drop_path_scale
 
 
@@ -237,11 +238,17 @@ class MultiScaleAttention(nn.Module):
             return None
         return ws, lns, strides
 
-    def attend(self, x, thw_shape):
-        """Everything before `proj`: returns (y [B, Lq, C], out_thw) with y = softmax(qkᵀ·scale)v (+q)."""
+    def attend(self, x, thw_shape, ln_in=None):
+        """Everything before `proj`: returns (y [B, Lq, C], out_thw) with y = softmax(qkᵀ·scale)v (+q).
+        ln_in = (norm1, row statistics of x): `x` is the RAW block stream and norm1 is folded into the qkv GEMM."""
         B, N, _ = x.shape
         C, h = self.dim_out, self.num_heads
-        qkv = AG.linear(x, self.qkv.weight, self.qkv.bias)
+        if ln_in is not None:
+            norm, stats = ln_in
+            wf, bf, colsum = weights.folded_ln_linear(self.qkv.weight, self.qkv.bias, norm.weight, norm.bias)
+            qkv = ops.linear_ln(x, stats, wf, bf, colsum, norm.eps)
+        else:
+            qkv = AG.linear(x, self.qkv.weight, self.qkv.bias)
         pool_params = [p for m in (self.pool_q, self.pool_k, self.pool_v, getattr(self, "norm_q", None),
                                    getattr(self, "norm_k", None), getattr(self, "norm_v", None)) if m is not None
                        for p in m.parameters()]
@@ -309,11 +316,17 @@ class MultiScaleAttention(nn.Module):
         y = ops.attention(q, k, v, self.scale, self.use_query_residual_pool)
         return y, out_shape
 
-    def forward(self, x, thw_shape, residual=None, row_scale=None):
+    def forward(self, x, thw_shape, residual=None, row_scale=None, ln_in=None, want_stats=False):
         """Reference contract: (x [B,N,dim], thw) -> (proj(attn) [B,Lq,dim_out], thw').
-        `residual` / `row_scale` (used by MultiScaleBlock) fold `x_res + drop_path(.)` into the proj GEMM."""
+        `residual` / `row_scale` (used by MultiScaleBlock) fold `x_res + drop_path(.)` into the proj GEMM.
+        ln_in / want_stats (eval, bf16; MultiScaleBlock only): norm1 folded into the qkv GEMM, and the proj epilogue emits
+        the row statistics norm2's folding needs."""
         dt = _compute_dtype(x)
-        y, out_shape = self.attend(x.to(dt), thw_shape)
+        y, out_shape = self.attend(x.to(dt), thw_shape, ln_in)
+        if want_stats:
+            out = ops.linear_stats(y, weights.cached_weight(self.proj.weight, y.dtype), self.proj.bias, residual=residual,
+                                   row_scale=row_scale)
+            return out, out_shape
         if self.drop_rate > 0.0 and self.training:
             # MVIT.DROPOUT_RATE > 0 (0.0 in every shipped config): the dropout mask sits between the GEMM and the
             # residual add, so the epilogue fusion is split and the elementwise tail is left to PyTorch
@@ -390,7 +403,12 @@ class MultiScaleBlock(nn.Module):
         s_attn = drop_path_scale(B, p_drop, self.training, x.device)
         s_mlp = drop_path_scale(B, p_drop, self.training, x.device)
 
-        xn = AG.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        # Eval / bf16: neither LayerNorm runs as a kernel.  The GEMM that produced the block stream (patch embed, the previous
+        # block's fc2, this block's proj) left per-row (sum, sum of squares) next to it; qkv and fc1 read the raw stream with
+        # gamma folded into their weights and finish the normalisation in their epilogues (gemm_tc.cu, kLnIn / kLnStats).
+        fold = self._ln_fold_ok(x)
+        stats1 = ops.row_stats_of(x) if fold else None
+        xn = x if stats1 is not None else AG.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         if self.expand_channel and not self.pool_skip_use_conv:
             x = AG.linear(x, self.proj_max_pool.weight, self.proj_max_pool.bias)
         if self._skip_is_identity():
@@ -398,10 +416,27 @@ class MultiScaleBlock(nn.Module):
         else:
             x_res, _ = attention_pool(x, self.pool_skip, thw_shape, has_cls_embed=self.has_cls_embed)
         # x = x_res + drop_path(proj(attn))  — residual and DropPath scale live in the proj GEMM epilogue
-        x, thw_new = self.attn(xn, thw_shape, residual=x_res, row_scale=s_attn)
+        x, thw_new = self.attn(xn, thw_shape, residual=x_res, row_scale=s_attn,
+                               ln_in=(self.norm1, stats1) if stats1 is not None else None, want_stats=fold)
+        stats2 = ops.row_stats_of(x) if fold and self.dim == self.dim_out else None
+        if stats2 is not None:
+            return self.mlp(x, residual=x, row_scale=s_mlp, ln_in=(self.norm2, stats2), want_stats=True), thw_new
         x_norm = AG.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         if self.dim != self.dim_out:
             x = AG.linear(x_norm, self.proj.weight, self.proj.bias)
         # out = x + drop_path(mlp(x_norm)) — residual and scale in the fc2 GEMM epilogue
-        out = self.mlp(x_norm, residual=x, row_scale=s_mlp)
+        out = self.mlp(x_norm, residual=x, row_scale=s_mlp, want_stats=fold)
         return out, thw_new
+
+    def _ln_fold_ok(self, x):
+        if not (ops.ln_fold_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and not self.has_cls_embed):
+            return False
+        if self.attn.drop_rate > 0.0 and self.training:
+            return False
+        params = [self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.attn.qkv.weight,
+                  self.attn.proj.weight, self.mlp.fc1.weight, self.mlp.fc2.weight]
+        if AG.recording(x, *params):
+            return False
+        # 16-byte TMA rows for every GEMM on the path
+        return all(d % 8 == 0 for d in (self.attn.qkv.in_features, self.attn.proj.out_features, self.mlp.fc1.out_features,
+                                        self.mlp.fc2.out_features))

@@ -5,6 +5,8 @@ import torch
 import torch.nn as nn
 
 from . import autograd as AG
+from . import ops
+from .weights import cached_weight, folded_ln_linear
 
 
 def drop_path_scale(batch: int, drop_prob: float, training: bool, device, dtype=torch.float32):
@@ -56,8 +58,19 @@ class Mlp(nn.Module):
         if not isinstance(self.act, nn.GELU) or getattr(self.act, "approximate", "none") != "none":
             raise NotImplementedError("the B200 MLP kernel fuses exact (erf) GELU only")
 
-    def forward(self, x, residual=None, row_scale=None):
-        """Returns fc2(gelu(fc1(x))) * row_scale + residual."""
+    def forward(self, x, residual=None, row_scale=None, ln_in=None, want_stats=False):
+        """Returns fc2(gelu(fc1(x))) * row_scale + residual.
+        ln_in = (norm2, row statistics of x): `x` is the raw block stream and norm2 is folded into fc1; want_stats: the
+        fc2 epilogue emits the row statistics of the result (eval / bf16, see MultiScaleBlock.forward)."""
+        if ln_in is not None or want_stats:
+            if ln_in is not None:
+                norm, stats = ln_in
+                wf, bf, colsum = folded_ln_linear(self.fc1.weight, self.fc1.bias, norm.weight, norm.bias)
+                h = ops.linear_ln(x, stats, wf, bf, colsum, norm.eps, gelu=True)
+            else:
+                h = AG.linear(x, self.fc1.weight, self.fc1.bias, gelu=True)
+            return ops.linear_stats(h, cached_weight(self.fc2.weight, h.dtype), self.fc2.bias, residual=residual,
+                                    row_scale=row_scale)
         if self.drop_rate > 0.0 and self.training:
             # dropout after the activation and after fc2 (common.py:28-33): un-fused elementwise tail, see attention.py
             h = self.drop(AG.linear(x, self.fc1.weight, self.fc1.bias, gelu=True))

@@ -107,7 +107,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         const __grid_constant__ CUtensorMap tmap_dq, DqParams p) {
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
+  // to LDS / STS instead of generic LD / ST
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sQ = smem;                                  // [2][24 KB]
   uint8_t *sdO = smem + 2 * kTile128;                  // [2][24 KB]
   uint8_t *sKV = smem + 4 * kTile128;                  // [stage][K 12 KB | V 12 KB]
@@ -334,7 +336,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                          DkvParams p) {
   using namespace dkv;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
+  // to LDS / STS instead of generic LD / ST
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sK = smem, *sV = smem + kTile128;
   uint8_t *sRing = smem + 2 * kTile128;                // [stage][Q 12 KB | dO 12 KB]
   uint8_t *sVec = sRing + kStages * kStageBytes;       // [stage][lse2 64 | delta 64]

@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
+  // to LDS / STS instead of generic LD / ST
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sQ = smem;                                  // [2][24 KB]
   uint8_t *sKV = smem + 2 * kQTileBytes;               // [stage][K 12 KB | V 12 KB]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * kStageBytes);

@@ -37,7 +37,7 @@ constexpr int kBoxBytes = BM * kBoxCols * 2;
 //                tile, so operand traffic from L2 per FLOP drops by 1.75x (the 1-CTA kernel is L2->SM bound at
 //                ~64 FLOP/B); accumulators live in both CTAs' TMEM, each CTA drains/stores its own 128 rows.
 template <int BN, bool PAIR> struct Cfg {
-  static constexpr int kStages = PAIR ? 4 : (BN == 128 ? 5 : 4);
+  static constexpr int kStages = 4;
   static constexpr int kNB = (PAIR || BN == 128) ? 2 : 4;  // in-place residual/output tile buffers
   static constexpr int kABytes = BM * BK * 2;              // 16 KB
   static constexpr int kBRows = PAIR ? BN / 2 : BN;        // w rows staged by one CTA
@@ -56,8 +56,22 @@ template <int BN, bool PAIR> struct Cfg {
   static constexpr int kCols = BN / kParts;                // columns of one epilogue thread: 48 (BN 192) / 32
   static constexpr int kChunk = kCols % 32 == 0 ? 32 : 16; // columns per tcgen05.ld
   static constexpr int kNumChunks = kCols / kChunk;        // 3 / 1
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + 2 * BN * 4 + 512 + 1024;
+  // bias | LayerNorm column-sum slices (double-buffered) + per-part row statistics staging
+  static constexpr int kVecBytes = 4 * BN * 4;
+  static constexpr int kStatBytes = kParts * BM * 8;
+  static constexpr int kLnMaxParts = 4;                    // N tiles of the producer (C <= 768 at 192 columns per tile)
+  static constexpr int kLnBytes = 2 * kLnMaxParts * BM * 8; // kLnIn: input-row statistics, double-buffered
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + kVecBytes + kStatBytes + kLnBytes + 512 + 1024;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory a CTA can opt into");
 };
+
+// LayerNorm folding (eval path).  The LayerNorm that FOLLOWS a block-stream GEMM (proj+residual, fc2+residual, patch embed)
+// and PRECEDES the next GEMM (qkv, fc1) is never run as a kernel:
+//   kLnStats: the producer's epilogue also emits, per output row and N tile, (sum, sum of squares) of the bf16 values it
+//             stores ([n_tiles][M][2] fp32, fixed summation order: reproducible);
+//   kLnIn:    the consumer reads the raw rows x, multiplies by w' = w.diag(gamma) (folded by the host) and its epilogue
+//             finishes the normalisation:  LN(x).w^T + b = rstd.(x.w'^T - mean.colsum(w')) + (b + w.beta).
+constexpr int kLnNone = 0, kLnIn = 1, kLnStats = 2;
 
 // Implicit-GEMM convolution mode (patch embedding): the A operand is a folded clip [B, Tf, Hf, Wf, Cf] read through a
 // 5-D tensor map; an M tile is an 8(w) x 8(h) x 2(t) patch of output tokens and k-block kb = (tap, 64-channel slice):
@@ -70,9 +84,30 @@ struct Params {
   int64_t M, rows_per_sample, res_period;
   int N, K, epilogue, has_residual;
   ConvGeom conv;
+  const float *colsum;        // kLnIn: sum_k w'[n, k]
+  const float2 *ln_stats;     // kLnIn: [ln_parts][M] (sum, sum of squares) of the input rows
+  float2 *stats_out;          // kLnStats: [n_tiles][M]
+  int ln_parts;
+  float ln_inv_c, ln_eps;
 };
 struct TileCoord { int b, t0, h0, w0; };
-__device__ __forceinline__ TileCoord conv_tile(const ConvGeom &g, int64_t mt) {
+// (m tile, n tile) of a persistent CTA's tile sequence t = tile0, tile0 + step, ...; t = m * n_tiles + n.  Advanced
+// incrementally: the 64-bit divisions of the closed form sat on every epilogue warp's critical path once per tile.
+struct TileWalk {
+  int m, n, dm, dn, n_tiles;
+  __device__ __forceinline__ TileWalk(int64_t tile0, int64_t step, int n_tiles_) : n_tiles(n_tiles_) {
+    m = (int)(tile0 / n_tiles_);
+    n = (int)(tile0 % n_tiles_);
+    dm = (int)(step / n_tiles_);
+    dn = (int)(step % n_tiles_);
+  }
+  __device__ __forceinline__ void next() {
+    m += dm;
+    n += dn;
+    if (n >= n_tiles) { n -= n_tiles; ++m; }
+  }
+};
+__device__ __forceinline__ TileCoord conv_tile(const ConvGeom &g, int mt) {
   TileCoord c;
   const int wq = g.Wf / 8, hq = g.Hf / 8, tq = g.Tf / 2;
   c.w0 = (int)(mt % wq) * 8; mt /= wq;
@@ -121,18 +156,23 @@ __device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
   return __fadd2_rn(cdf, xpdf);
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int LNM>
 __global__ void __launch_bounds__((Cfg<BN, PAIR>::kThreads), 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, Params p) {
   using C = Cfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
+  // to LDS / STS instead of generic LD / ST
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sA = smem;
   uint8_t *sB = smem + C::kStages * C::kABytes;
   uint8_t *sOut = smem + C::kStages * C::kStageBytes;
-  float *sBias = reinterpret_cast<float *>(sOut + C::kNB * C::kOutBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 2 * BN);   // sBias is double-buffered
+  float *sBias = reinterpret_cast<float *>(sOut + C::kNB * C::kOutBytes);   // [2][BN] bias, then [2][BN] colsum
+  float *sCol = sBias + 2 * BN;
+  float2 *sStat = reinterpret_cast<float2 *>(sBias + 4 * BN);                // [kParts][BM]
+  float2 *sLn = sStat + C::kParts * BM;                                      // [2][kLnMaxParts][BM]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sLn + 2 * C::kLnMaxParts * BM);
   uint64_t *full = bars, *empty = full + C::kStages, *tfull = empty + C::kStages, *tempty = tfull + 2;
   uint64_t *res_full = tempty + 2, *buf_free = res_full + C::kNB;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(buf_free + C::kNB);
@@ -188,8 +228,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = tile0; t < tiles; t += tile_step) {
-        const int m0 = (int)(t / n_tiles) * TM + (int)rank * BM, n0 = (int)(t % n_tiles) * BN;
+      TileWalk tw(tile0, tile_step, n_tiles);
+      for (int64_t t = tile0; t < tiles; t += tile_step, tw.next()) {
+        const int m0 = tw.m * TM + (int)rank * BM, n0 = tw.n * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if constexpr (PAIR) {
@@ -200,7 +241,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           } else {
             mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
             if (p.conv.enabled) {
-              const TileCoord tc = conv_tile(p.conv, t / n_tiles);
+              const TileCoord tc = conv_tile(p.conv, tw.m);
               const int tap = kb / p.conv.cblocks, kc = kb - tap * p.conv.cblocks;
               const int dw = p.conv.lo_w + tap % p.conv.nw, dh = p.conv.lo_h + (tap / p.conv.nw) % p.conv.nh,
                         dt = p.conv.lo_t + tap / (p.conv.nw * p.conv.nh);
@@ -254,14 +295,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       int buf = 0;
       uint32_t phase = 0;
-      for (int64_t t = tile0; t < tiles; t += tile_step) {
+      TileWalk tw(tile0, tile_step, n_tiles);
+      for (int64_t t = tile0; t < tiles; t += tile_step, tw.next()) {
         mbar_wait(&buf_free[buf], phase ^ 1);         // the TMA store that last used this buffer has read it
         if (p.has_residual) {
-          const int64_t mrow = (t / n_tiles) * TM + rank * BM;
-          const int m0 = (int)(p.res_period ? mrow % p.res_period : mrow), n0 = (int)(t % n_tiles) * BN;
+          const int64_t mrow = (int64_t)tw.m * TM + rank * BM;
+          const int m0 = (int)(p.res_period ? mrow % p.res_period : mrow), n0 = tw.n * BN;
           mbar_arrive_expect_tx(&res_full[buf], C::kOutBytes);
           if (p.conv.enabled) {                         // positional table [Tf, Hf, Wf, N], same patch, no batch axis
-            const TileCoord tc = conv_tile(p.conv, t / n_tiles);
+            const TileCoord tc = conv_tile(p.conv, tw.m);
 #pragma unroll
             for (int bx = 0; bx < C::kBoxes; ++bx)
               tma_load_4d(sOut + buf * C::kOutBytes + bx * kBoxBytes, &tmap_r, &res_full[buf], n0 + bx * kBoxCols, tc.w0,
@@ -289,23 +331,60 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint32_t acc_phase = 0, buf_phase = 0;
     int64_t it = 0;
     // bias slice of the first tile; later slices are fetched one tile ahead (global latency off the critical path)
+    TileWalk tw(tile0, tile_step, n_tiles), tw_next = tw;
+    tw_next.next();
     if (et < BN) {
-      const int n = (int)(tile0 % n_tiles) * BN + et;
+      const int n = tw.n * BN + et;
       sBias[et] = (p.bias && tile0 < tiles && n < p.N) ? p.bias[n] : 0.f;
+      if constexpr (LNM == kLnIn) sCol[et] = (tile0 < tiles && n < p.N) ? p.colsum[n] : 0.f;
     }
-    for (int64_t t = tile0; t < tiles; t += tile_step, ++it) {
-      const int64_t m0 = (t / n_tiles) * TM + rank * BM;
-      const int n0 = (int)(t % n_tiles) * BN;
-      const float *bias_s = sBias + (it & 1) * BN;
-      float bias_next = 0.f;
-      const int64_t tn = t + tile_step;
-      if (et < BN && tn < tiles && p.bias) {
-        const int n = (int)(tn % n_tiles) * BN + et;
-        if (n < p.N) bias_next = p.bias[n];
+    // kLnIn: (sum, sum of squares) of the 128 input rows of a tile, one slice per N tile of the producer.  Fetched one tile
+    // ahead with cp.async by the first four epilogue warps (et == row), so no thread ever waits on the L2 round trip.
+    auto fetch_row_stats = [&](int m_tile, int slot) {
+      if (et < BM) {
+        const int64_t m = min((int64_t)m_tile * TM + rank * BM + et, p.M - 1);
+        for (int i = 0; i < p.ln_parts; ++i)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sLn + (slot * C::kLnMaxParts + i) * BM + et)),
+                       "l"(p.ln_stats + (int64_t)i * p.M + m) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if constexpr (LNM == kLnIn) {
+      if (tile0 < tiles) fetch_row_stats(tw.m, 0);
+    }
+    for (int64_t t = tile0; t < tiles; t += tile_step, ++it, tw.next(), tw_next.next()) {
+      const int64_t m0 = (int64_t)tw.m * TM + rank * BM;
+      const int n0 = tw.n * BN;
+      const float *bias_s = sBias + (it & 1) * BN;
+      const float *col_s = sCol + (it & 1) * BN;
+      float bias_next = 0.f, col_next = 0.f;
+      const int64_t tn = t + tile_step;
+      if (et < BN && tn < tiles) {
+        const int n = tw_next.n * BN + et;
+        if (n < p.N) {
+          if (p.bias) bias_next = p.bias[n];
+          if constexpr (LNM == kLnIn) col_next = p.colsum[n];
+        }
+      }
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);   // kLnStats
+      if constexpr (LNM == kLnIn) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this tile's statistics have landed
       float rs = 1.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + row, p.M - 1) / p.rows_per_sample];
       asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");   // this tile's bias slice is visible; previous store was issued
+      float ln_a = 1.f, ln_b = 0.f;                      // x_norm . w'^T = ln_a * acc + ln_b * colsum
+      if constexpr (LNM == kLnIn) {
+        const float2 *sl = sLn + (int)(it & 1) * C::kLnMaxParts * BM + row;
+        float2 st = sl[0];
+        for (int i = 1; i < p.ln_parts; ++i) {           // fixed order: reproducible
+          st.x += sl[i * BM].x;
+          st.y += sl[i * BM].y;
+        }
+        if (tn < tiles) fetch_row_stats(tw_next.m, (int)((it + 1) & 1));   // readers of that slot passed bar.sync 1 a tile ago
+        const float mean = st.x * p.ln_inv_c;
+        const float var = fmaxf(st.y * p.ln_inv_c - mean * mean, 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = -mean * ln_a;
+      }
       mbar_wait(&res_full[buf], buf_phase);            // buffer is ours (and holds the residual tile, if any)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -326,10 +405,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const int col = col0 + v * 8;
           const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + col);
           const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + col + 4);
-          float2 x[4] = {make_float2(__uint_as_float(r[c][v * 8 + 0]) + b0.x, __uint_as_float(r[c][v * 8 + 1]) + b0.y),
-                         make_float2(__uint_as_float(r[c][v * 8 + 2]) + b0.z, __uint_as_float(r[c][v * 8 + 3]) + b0.w),
-                         make_float2(__uint_as_float(r[c][v * 8 + 4]) + b1.x, __uint_as_float(r[c][v * 8 + 5]) + b1.y),
-                         make_float2(__uint_as_float(r[c][v * 8 + 6]) + b1.z, __uint_as_float(r[c][v * 8 + 7]) + b1.w)};
+          float2 x[4];
+          if constexpr (LNM == kLnIn) {
+            const float4 c0 = *reinterpret_cast<const float4 *>(col_s + col);
+            const float4 c1 = *reinterpret_cast<const float4 *>(col_s + col + 4);
+            const float2 m2 = make_float2(ln_b, ln_b);
+            const float2 sh[4] = {__ffma2_rn(m2, make_float2(c0.x, c0.y), make_float2(b0.x, b0.y)),
+                                  __ffma2_rn(m2, make_float2(c0.z, c0.w), make_float2(b0.z, b0.w)),
+                                  __ffma2_rn(m2, make_float2(c1.x, c1.y), make_float2(b1.x, b1.y)),
+                                  __ffma2_rn(m2, make_float2(c1.z, c1.w), make_float2(b1.z, b1.w))};
+            // scalar FMAs on the accumulator words: pairing the tcgen05.ld destination registers for a packed FMA costs a
+            // register move per element
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              x[j] = make_float2(fmaf(__uint_as_float(r[c][v * 8 + 2 * j]), ln_a, sh[j].x),
+                                 fmaf(__uint_as_float(r[c][v * 8 + 2 * j + 1]), ln_a, sh[j].y));
+          } else {
+            x[0] = make_float2(__uint_as_float(r[c][v * 8 + 0]) + b0.x, __uint_as_float(r[c][v * 8 + 1]) + b0.y);
+            x[1] = make_float2(__uint_as_float(r[c][v * 8 + 2]) + b0.z, __uint_as_float(r[c][v * 8 + 3]) + b0.w);
+            x[2] = make_float2(__uint_as_float(r[c][v * 8 + 4]) + b1.x, __uint_as_float(r[c][v * 8 + 5]) + b1.y);
+            x[3] = make_float2(__uint_as_float(r[c][v * 8 + 6]) + b1.z, __uint_as_float(r[c][v * 8 + 7]) + b1.w);
+          }
           if (p.epilogue == MVIT_EPI_GELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = gelu_fast2(x[j]);
@@ -365,11 +461,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat162 h = __floats2bfloat162_rn(x[j].x, x[j].y);
             o[j] = *reinterpret_cast<uint32_t *>(&h);
+            if constexpr (LNM == kLnStats) {                     // statistics of exactly the values the next GEMM reads
+              const float2 f = make_float2(__uint_as_float(o[j] << 16), __uint_as_float(o[j] & 0xffff0000u));
+              sum2 = __fadd2_rn(sum2, f);
+              sq2 = __ffma2_rn(f, f, sq2);
+            }
           }
           *slot = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
-      if (et < BN) sBias[((it + 1) & 1) * BN + et] = bias_next;   // readers of that half finished a tile ago
+      if constexpr (LNM == kLnStats) sStat[hf * BM + row] = make_float2(sum2.x + sum2.y, sq2.x + sq2.y);
+      if (et < BN) {                                             // readers of that half finished a tile ago
+        sBias[((it + 1) & 1) * BN + et] = bias_next;
+        if constexpr (LNM == kLnIn) sCol[((it + 1) & 1) * BN + et] = col_next;
+      }
       // accumulator fully read -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -381,9 +486,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // tile is complete in shared memory -> one thread TMA-stores it
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, %0;" ::"n"(C::kEpiThreads) : "memory");
+      if constexpr (LNM == kLnStats) {
+        if (et < BM) {                                           // et == row for the first four epilogue warps
+          float2 tot = sStat[et];
+#pragma unroll
+          for (int i = 1; i < C::kParts; ++i) {
+            const float2 v = sStat[i * BM + et];
+            tot.x += v.x;
+            tot.y += v.y;
+          }
+          int64_t token = m0 + et;
+          if (p.conv.enabled) {                                  // tile row -> token of the 8(w) x 8(h) x 2(t) patch
+            const TileCoord tc = conv_tile(p.conv, tw.m);
+            token = (((int64_t)tc.b * p.conv.Tf + tc.t0 + (et >> 6)) * p.conv.Hf + tc.h0 + ((et >> 3) & 7)) * p.conv.Wf +
+                    tc.w0 + (et & 7);
+          }
+          if (token < p.M) p.stats_out[(int64_t)tw.n * p.M + token] = tot;
+        }
+      }
       if (et == 0) {
         if (p.conv.enabled) {
-          const TileCoord tc = conv_tile(p.conv, t / n_tiles);
+          const TileCoord tc = conv_tile(p.conv, tw.m);
 #pragma unroll
           for (int bx = 0; bx < C::kBoxes; ++bx)
             if (n0 + bx * kBoxCols < p.N)
@@ -460,7 +583,7 @@ bool linear_tc_supported(const LinearArgs &a, const char **why) {
   return true;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int LNM>
 static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   using C = gemm::Cfg<BN, PAIR>;
   CUtensorMap tx, tw, ty, tr;
@@ -481,8 +604,10 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   } else {
     tr = ty;
   }
-  MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<BN, PAIR>), C::kSmemBytes);
-  gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0, {}};
+  MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<BN, PAIR, LNM>), C::kSmemBytes);
+  gemm::Params p{a.bias, a.row_scale, a.M, a.rows_per_sample, a.res_period, a.N, a.K, a.epilogue, a.residual ? 1 : 0, {},
+                 a.colsum, reinterpret_cast<const float2 *>(a.ln_stats), reinterpret_cast<float2 *>(a.stats_out),
+                 a.ln_parts, 1.0f / (float)a.K, a.ln_eps};
   constexpr int TM = PAIR ? 2 * gemm::BM : gemm::BM;
   const int64_t tiles = ((a.M + TM - 1) / TM) * ((a.N + BN - 1) / BN);
   cudaLaunchConfig_t cfg{};
@@ -501,14 +626,14 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
-  MVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm::linear_tc_kernel<BN, PAIR>, tx, tw, ty, tr, p));
+  MVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm::linear_tc_kernel<BN, PAIR, LNM>, tx, tw, ty, tr, p));
   return 0;
 }
 
 // Patch-embedding convolution as an implicit GEMM over the folded clip (see ConvGeom).  M = B*Tf*Hf*Wf tokens,
 // K = taps * Cf, N = Cout; tile = <96, false>.
-int patch_conv_tc(const void *folded, const void *wf, const float *bias, const void *pos, void *out, int B, int Tf,
-                  int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N, cudaStream_t st) {
+int patch_conv_tc(const void *folded, const void *wf, const float *bias, const void *pos, void *out, float *stats_out, int B,
+                  int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N, cudaStream_t st) {
   using C = gemm::Cfg<96, false>;
   MVIT_REQUIRE(Tf % 2 == 0 && Hf % 8 == 0 && Wf % 8 == 0, "patch_conv: token grid must be a multiple of 2x8x8");
   MVIT_REQUIRE(Cf % gemm::BK == 0 && N % 8 == 0, "patch_conv: folded channels must be a multiple of 64, Cout of 8");
@@ -539,25 +664,91 @@ int patch_conv_tc(const void *folded, const void *wf, const float *bias, const v
       tr = ty;
     }
   }
-  MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<96, false>), C::kSmemBytes);
   const int64_t M = (int64_t)B * Tf * Hf * Wf;
   gemm::Params p{bias, nullptr, M, 0, 0, N, K, MVIT_EPI_NONE, pos ? 1 : 0,
-                 {1, Tf, Hf, Wf, Cf / gemm::BK, nt, nh, nw, lo_t, lo_h, lo_w}};
+                 {1, Tf, Hf, Wf, Cf / gemm::BK, nt, nh, nw, lo_t, lo_h, lo_w},
+                 nullptr, nullptr, reinterpret_cast<float2 *>(stats_out), 0, 0.f, 0.f};
   const int64_t tiles = (M / gemm::BM) * ((N + 95) / 96);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
-  gemm::linear_tc_kernel<96, false><<<grid, C::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+  if (stats_out) {
+    MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<96, false, gemm::kLnStats>), C::kSmemBytes);
+    gemm::linear_tc_kernel<96, false, gemm::kLnStats><<<grid, C::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+  } else {
+    MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<96, false, gemm::kLnNone>), C::kSmemBytes);
+    gemm::linear_tc_kernel<96, false, gemm::kLnNone><<<grid, C::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+  }
   MVIT_LAUNCH_OK("patch_conv(tcgen05)");
   return 0;
 }
 
+// tile configuration: compute-bound shapes (long K): CTA pairs on 256x192 tiles, else 128x128; memory-bound shapes:
+// 128x96 tiles with a deeper output ring
+static int pick_cfg(int64_t M, int N, int K) {
+  if (K >= 384 && N % 192 == 0 && ((M + 255) / 256) * (N / 192) >= num_sms() / 2) return 2;
+  if (K >= 384 && N % 128 == 0 && ((M + 127) / 128) * (N / 128) >= num_sms()) return 1;
+  return 0;
+}
+
+int linear_tc_stat_parts(int64_t M, int N, int K) {
+  const int bn = pick_cfg(M, N, K) == 2 ? 192 : (pick_cfg(M, N, K) == 1 ? 128 : 96);
+  return (N + bn - 1) / bn;
+}
+
+template <int LNM>
+static int linear_tc_mode(const LinearArgs &a, cudaStream_t st) {
+  switch (pick_cfg(a.M, a.N, a.K)) {
+    case 2: return launch_tc<192, true, LNM>(a, st);
+    case 1: return launch_tc<128, false, LNM>(a, st);
+    default: return launch_tc<96, false, LNM>(a, st);
+  }
+}
+
 int linear_tc(const LinearArgs &a, cudaStream_t st) {
-  // compute-bound shapes (long K): CTA pairs on 256x192 tiles, else 128x128; memory-bound shapes: 128x96 tiles
-  // with a deeper output ring
-  if (a.K >= 384 && a.N % 192 == 0 && ((a.M + 255) / 256) * (a.N / 192) >= num_sms() / 2) return launch_tc<192, true>(a, st);
-  if (a.K >= 384 && a.N % 128 == 0 && ((a.M + 127) / 128) * (a.N / 128) >= num_sms()) return launch_tc<128, false>(a, st);
-  return launch_tc<96, false>(a, st);
+  MVIT_REQUIRE(!(a.ln_stats && a.stats_out), "linear: LayerNorm-folded input and row statistics output cannot be combined");
+  if (a.ln_stats) {
+    MVIT_REQUIRE(a.colsum && a.ln_parts > 0 && a.ln_parts <= 4, "linear: ln_stats needs colsum and 1..4 parts");
+    MVIT_REQUIRE(a.epilogue != MVIT_EPI_GELU_GRAD, "linear: the LayerNorm-folded input is a forward-only form");
+    return linear_tc_mode<gemm::kLnIn>(a, st);
+  }
+  if (a.stats_out) {
+    MVIT_REQUIRE(a.epilogue == MVIT_EPI_NONE, "linear: row statistics are emitted by plain (+residual) epilogues only");
+    MVIT_REQUIRE(a.ldy == a.N, "linear: row statistics need a dense output (ldy == N)");
+    return linear_tc_mode<gemm::kLnStats>(a, st);
+  }
+  return linear_tc_mode<gemm::kLnNone>(a, st);
 }
 
 int gemm_tc_fault_take() { return tc_fault_take(); }
 
 }  // namespace mvit
+
+/* See include/mvit_b200.h. */
+extern "C" int mvit_linear_stat_parts(int64_t M, int N, int K) {
+  if (M < 0 || N <= 0 || K <= 0) return -1;
+  return mvit::linear_tc_stat_parts(M, N, K);
+}
+
+extern "C" int mvit_linear_ln_fwd(const void *x, const void *w, const float *bias, const float *colsum,
+                                  const float *ln_stats, int ln_parts, float ln_eps, const void *residual,
+                                  const float *row_scale, int64_t rows_per_sample, void *y, float *stats_out, int64_t M,
+                                  int N, int K, int64_t ldy, int64_t ldr, int epilogue, void *stream) {
+  using namespace mvit;
+  MVIT_REQUIRE(x && w && y, "linear_ln: null pointer");
+  MVIT_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_ln: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  MVIT_REQUIRE(epilogue == MVIT_EPI_NONE || epilogue == MVIT_EPI_GELU, "linear_ln: epilogue must be NONE or GELU");
+  MVIT_REQUIRE((ln_stats != nullptr) != (stats_out != nullptr), "linear_ln: exactly one of ln_stats / stats_out must be set");
+  MVIT_REQUIRE(ldy >= N && (!residual || ldr >= N), "linear_ln: leading dimension smaller than N");
+  MVIT_REQUIRE(!row_scale || rows_per_sample > 0, "linear_ln: row_scale needs rows_per_sample");
+  auto al8 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+  MVIT_REQUIRE(al8(ln_stats) && al8(stats_out), "linear_ln: statistics buffers must be 8-byte aligned");
+  if (M == 0) return 0;
+  LinearArgs a{x, w, residual, bias, row_scale, y, M, rows_per_sample, ldy, ldr, 0, N, K, epilogue};
+  a.colsum = colsum;
+  a.ln_stats = ln_stats;
+  a.ln_parts = ln_parts;
+  a.ln_eps = ln_eps;
+  a.stats_out = stats_out;
+  const char *why = "";
+  MVIT_REQUIRE(linear_tc_supported(a, &why), "linear_ln: tcgen05 path rejected: %s (there is no other implementation)", why);
+  return linear_tc(a, static_cast<cudaStream_t>(stream));
+}

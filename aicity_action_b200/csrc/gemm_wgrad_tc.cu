@@ -35,7 +35,9 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
                        int q_tiles) {
   using C = Cfg<BQ>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
+  // to LDS / STS instead of generic LD / ST
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes);
   uint64_t *full = bars, *empty = bars + C::kStages, *done = empty + C::kStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);

@@ -412,13 +412,27 @@ extern "C" int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, 
   return 0;
 }
 
-extern "C" int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out,
-                                   int B, int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h,
-                                   int lo_w, int N, void *stream) {
+static int patch_conv_entry(const void *folded, const void *wf, const float *bias, const void *pos, void *out, float *stats_out,
+                            int B, int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N,
+                            void *stream) {
   using namespace mvit;
   MVIT_REQUIRE(folded && wf && out, "patch_conv: null pointer");
   MVIT_REQUIRE(B >= 0 && Tf > 0 && Hf > 0 && Wf > 0 && nt > 0 && nh > 0 && nw > 0 && N > 0, "patch_conv: bad shape");
+  MVIT_REQUIRE((reinterpret_cast<uintptr_t>(stats_out) & 7) == 0, "patch_conv: stats_out must be 8-byte aligned");
   if (B == 0) return 0;
-  return patch_conv_tc(folded, wf, bias, pos, out, B, Tf, Hf, Wf, Cf, nt, nh, nw, lo_t, lo_h, lo_w, N,
+  return patch_conv_tc(folded, wf, bias, pos, out, stats_out, B, Tf, Hf, Wf, Cf, nt, nh, nw, lo_t, lo_h, lo_w, N,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out,
+                                   int B, int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h,
+                                   int lo_w, int N, void *stream) {
+  return patch_conv_entry(folded, wf, bias, pos, out, nullptr, B, Tf, Hf, Wf, Cf, nt, nh, nw, lo_t, lo_h, lo_w, N, stream);
+}
+
+extern "C" int mvit_patch_conv_stats_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out,
+                                         float *stats_out, int B, int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw,
+                                         int lo_t, int lo_h, int lo_w, int N, void *stream) {
+  MVIT_REQUIRE(stats_out, "patch_conv_stats: stats_out is NULL");
+  return patch_conv_entry(folded, wf, bias, pos, out, stats_out, B, Tf, Hf, Wf, Cf, nt, nh, nw, lo_t, lo_h, lo_w, N, stream);
 }

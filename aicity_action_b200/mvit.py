@@ -108,7 +108,7 @@ class PatchEmbed(nn.Module):
             return False
         return out[0] % 2 == 0 and out[1] % 8 == 0 and out[2] % 8 == 0 and self.proj.out_channels % 8 == 0
 
-    def forward(self, x, dtype=None, pos=None, pos_period=0):
+    def forward(self, x, dtype=None, pos=None, pos_period=0, want_stats=False):
         """x: [B, C, T, H, W] clip (or [B, C, H, W] for conv_2d; or uint8 frames [B, T, H, W, C], normalised on the
         fly) -> tokens [B, L, Cout].  bf16: space-to-depth fold + implicit-GEMM convolution on tensor cores (5-D TMA,
         no im2col matrix); otherwise im2col + GEMM.  `pos` ([L, Cout] table in the activation dtype) and the bias are
@@ -119,7 +119,7 @@ class PatchEmbed(nn.Module):
         if self._conv_path_ok(x, dtype):
             _, s, _, lo, taps, _, cf = self._fold_geometry()
             folded = ops.fold_clip(x, s, cf)
-            return ops.patch_conv(folded, self._folded_weight(), self.proj.bias, pos, taps, lo)
+            return ops.patch_conv(folded, self._folded_weight(), self.proj.bias, pos, taps, lo, want_stats=want_stats)
         if x.dtype == torch.uint8:
             x = ops.preprocess_u8(x, dtype)
         t3 = lambda v: [1] + list(v) if self.conv_2d else list(v)
@@ -401,7 +401,10 @@ class MViT(nn.Module):
         elif self.sep_pos_embed and not self.cls_embed_on:
             # bias + positional embedding ride in the patch-embed GEMM epilogue
             pos = self._pos_tokens(dtype)
-            x = self.patch_embed(x, dtype, pos=pos, pos_period=pos.shape[0])
+            # (eval / bf16: the epilogue also leaves the tokens' row statistics for block 0's folded norm1)
+            x = self.patch_embed(x, dtype, pos=pos, pos_period=pos.shape[0],
+                                 want_stats=ops.ln_fold_enabled() and self.norm_stem is None
+                                 and not (self.drop_rate and self.training))
         else:
             tokens = self.patch_embed(x, dtype)                  # [B, N, C]
             B = tokens.shape[0]

@@ -6,6 +6,8 @@ is no CPU implementation in the product (the CPU oracle lives in oracle/ and is 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -133,6 +135,77 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                                           EPI_GELU_GRAD if gelu_grad else (EPI_GELU if gelu else EPI_NONE), _dt(x), impl,
                                           _stream()),
               "mvit_linear_fwd")
+    launch_count += 1
+    return y
+
+
+STATS_ATTR = "_b200_row_stats"      # tensor attribute: [parts, M, 2] fp32 (sum, sum of squares) of the tensor's rows
+
+
+def ln_fold_enabled() -> bool:
+    """LayerNorm folding of the eval path ($MVIT_B200_LN_FOLD, default on)."""
+    return os.environ.get("MVIT_B200_LN_FOLD", "1") not in ("0", "false", "off")
+
+
+def row_stats_of(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """Row statistics a producing GEMM attached to `x` (None when `x` did not come straight out of one)."""
+    st = getattr(x, STATS_ATTR, None)
+    if st is None or st.shape[1] != x.numel() // x.shape[-1] or st.device != x.device:
+        return None
+    return st
+
+
+def linear_stats(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                 residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ops.linear (no activation) that also emits the per-row (sum, sum of squares) of its bf16 output and attaches them
+    to the result (`row_stats_of`): the producer half of the folded LayerNorm.  bf16 / tcgen05 only."""
+    global launch_count
+    _need_cuda(x, w, bias, residual, row_scale)
+    x = x.contiguous()
+    K, N = x.shape[-1], w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == x.dtype and w.shape[1] == K and w.is_contiguous()
+    M = x.numel() // K
+    y = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.numel() == M * N and residual.dtype == x.dtype
+    rows_per_sample = 0
+    if row_scale is not None:
+        row_scale = _f32c(row_scale).reshape(-1)
+        assert M % row_scale.numel() == 0
+        rows_per_sample = M // row_scale.numel()
+    bias = _f32c(bias)
+    lib = _lib.load()
+    parts = lib.mvit_linear_stat_parts(M, N, K)
+    stats = torch.empty((parts, M, 2), dtype=torch.float32, device=x.device)
+    with _Timed("linear", 2.0 * M * N * K):
+        check(lib.mvit_linear_ln_fwd(_ptr(x), _ptr(w), _ptr(bias), None, None, 0, 0.0, _ptr(residual), _ptr(row_scale),
+                                     rows_per_sample, _ptr(y), _ptr(stats), M, N, K, N, N, EPI_NONE, _stream()),
+              "mvit_linear_ln_fwd")
+    launch_count += 1
+    if parts > 4:        # the consumer stages at most 4 slices per row (small M on 128x96 tiles: wide rows span more N tiles)
+        stats = stats.sum(dim=0, keepdim=True)
+    setattr(y, STATS_ATTR, stats)
+    return y
+
+
+def linear_ln(x: torch.Tensor, stats: torch.Tensor, w_folded: torch.Tensor, bias_folded: torch.Tensor,
+              colsum: torch.Tensor, eps: float, *, gelu: bool = False) -> torch.Tensor:
+    """LayerNorm(x)·Wᵀ + b from the RAW rows `x` and their statistics: the consumer half of the folded LayerNorm
+    (`w_folded`, `bias_folded`, `colsum` from weights.folded_ln_linear)."""
+    global launch_count
+    _need_cuda(x, stats, w_folded, bias_folded, colsum)
+    x = x.contiguous()
+    K, N = x.shape[-1], w_folded.shape[0]
+    M = x.numel() // K
+    assert x.dtype == torch.bfloat16 and w_folded.dtype == x.dtype and w_folded.shape[1] == K and w_folded.is_contiguous()
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and tuple(stats.shape[1:]) == (M, 2)
+    assert bias_folded.dtype == torch.float32 and colsum.dtype == torch.float32
+    y = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+    with _Timed("linear", 2.0 * M * N * K):
+        check(_lib.load().mvit_linear_ln_fwd(_ptr(x), _ptr(w_folded), _ptr(bias_folded), _ptr(colsum), _ptr(stats),
+                                             stats.shape[0], float(eps), None, None, 0, _ptr(y), None, M, N, K, N, N,
+                                             EPI_GELU if gelu else EPI_NONE, _stream()), "mvit_linear_ln_fwd")
     launch_count += 1
     return y
 
@@ -399,8 +472,9 @@ def fold_clip(clip: torch.Tensor, stride: Sequence[int], Cf: int, mean: float = 
 
 
 def patch_conv(folded: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], pos: Optional[torch.Tensor],
-               taps: Sequence[int], lows: Sequence[int]) -> torch.Tensor:
-    """Implicit-GEMM patch embedding on the folded clip: returns tokens [B, Tf*Hf*Wf, N] (bf16)."""
+               taps: Sequence[int], lows: Sequence[int], want_stats: bool = False) -> torch.Tensor:
+    """Implicit-GEMM patch embedding on the folded clip: returns tokens [B, Tf*Hf*Wf, N] (bf16).  want_stats: also emit
+    the tokens' row statistics (`row_stats_of`) for the folded LayerNorm of the first block."""
     global launch_count
     _need_cuda(folded, wf, bias, pos)
     B, Tf, Hf, Wf, Cf = folded.shape
@@ -409,6 +483,15 @@ def patch_conv(folded: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tens
     assert wf.shape[1] == taps[0] * taps[1] * taps[2] * Cf
     out = torch.empty((B, Tf * Hf * Wf, N), dtype=torch.bfloat16, device=folded.device)
     bias = _f32c(bias)
+    if want_stats:
+        stats = torch.empty(((N + 95) // 96, B * Tf * Hf * Wf, 2), dtype=torch.float32, device=folded.device)
+        with _Timed("patch_conv", 2.0 * B * Tf * Hf * Wf * N * wf.shape[1]):
+            check(_lib.load().mvit_patch_conv_stats_fwd(_ptr(folded), _ptr(wf), _ptr(bias), _ptr(pos), _ptr(out), _ptr(stats),
+                                                        B, Tf, Hf, Wf, Cf, taps[0], taps[1], taps[2], lows[0], lows[1],
+                                                        lows[2], N, _stream()), "mvit_patch_conv_stats_fwd")
+        launch_count += 1
+        setattr(out, STATS_ATTR, stats)
+        return out
     with _Timed("patch_conv", 2.0 * B * Tf * Hf * Wf * N * wf.shape[1]):
         check(_lib.load().mvit_patch_conv_fwd(_ptr(folded), _ptr(wf), _ptr(bias), _ptr(pos), _ptr(out), B, Tf, Hf, Wf, Cf,
                                               taps[0], taps[1], taps[2], lows[0], lows[1], lows[2], N, _stream()),

@@ -65,7 +65,7 @@ def invalidate_caches(module: torch.nn.Module) -> int:
     version counter, e.g. `p.data.copy_()`).  Returns the number of parameters touched."""
     n = 0
     for p in module.parameters():
-        if hasattr(p, _ATTR) or hasattr(p, _ATTR + "_t"):
+        if hasattr(p, _ATTR) or hasattr(p, _ATTR + "_t") or hasattr(p, _ATTR + "_ln"):
             setattr(p, _STALE, getattr(p, _STALE, 0) + 1)
             n += 1
     for m in module.modules():                   # module-level caches (patch-embed GEMM weights, pos-embed table)
@@ -97,3 +97,32 @@ def cached_weight_t(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     dx = dy · W (a Linear whose weight is Wᵀ).  Cached like `cached_weight`."""
     key = (dtype, param._version, param.device, param.data_ptr(), _GENERATION)
     return _refresh(param, _ATTR + "_t", key, lambda: param.detach().t())
+
+
+def folded_ln_linear(weight: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor):
+    """Operands of the LayerNorm-folded Linear (ops.linear_ln):  LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·colsum) + b'  with
+    W' = W·diag(γ) rounded to bf16, colsum[n] = Σ_k W'[n,k] (of the ROUNDED values, so the mean correction cancels exactly
+    what the tensor core summed) and b' = b + W·β in fp32.  Cached on `weight`, keyed on the versions of all four
+    parameters; refreshed in place so captured graphs keep reading valid memory."""
+    ps = [weight, bias, gamma, beta]
+    key = tuple((p._version, p.data_ptr()) if p is not None else None for p in ps) + (weight.device, _GENERATION)
+    slot = getattr(weight, _ATTR + "_ln", None)
+    stale = getattr(weight, _STALE, 0)
+    if slot is not None and slot[0] == key and slot[2] == stale:
+        return slot[1]
+    with torch.no_grad():
+        w32 = weight.detach().float()
+        wf = (w32 * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        colsum = wf.float().sum(dim=1).contiguous()
+        bf = w32 @ beta.detach().float()
+        if bias is not None:
+            bf = bf + bias.detach().float()
+        bf = bf.contiguous()
+    if slot is not None and slot[1][0].shape == wf.shape and slot[1][0].device == wf.device:
+        for dst, src in zip(slot[1], (wf, bf, colsum)):
+            dst.copy_(src)
+        fresh = slot[1]
+    else:
+        fresh = (wf, bf, colsum)
+    setattr(weight, _ATTR + "_ln", (key, fresh, stale))
+    return fresh

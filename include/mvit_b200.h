@@ -84,6 +84,24 @@ int mvit_linear_fwd(const void *x, const void *w, const float *bias, const void 
                     int dtype, int impl, void *stream);
 
 /*
+ * LayerNorm folded around the Linear layers of a block (eval path, bf16, tcgen05 only; there is no other implementation).
+ * Replaces: norm1 -> attn.qkv (attention.py:421,231) and norm2 -> mlp.fc1 (attention.py:436, common.py:27) without a
+ * LayerNorm kernel and without materialising the normalised tensor.  Exactly one of {stats_out, ln_stats} is set:
+ *   producer form (stats_out != NULL): y = (x.w^T + bias)*row_scale + residual as mvit_linear_fwd, and additionally
+ *     stats_out[p][m] = (sum_n, sum_n^2) over the columns of N tile p of the bf16 values stored in row m;
+ *     stats_out: [mvit_linear_stat_parts(M, N, K)][M][2] fp32.
+ *   consumer form (ln_stats != NULL): x is the RAW block stream, ln_stats[ln_parts][M][2] its row statistics from a
+ *     producer, w = W.diag(gamma) (bf16), colsum[n] = sum_k w[n,k] (fp32, of the bf16 values), bias = b + W.beta:
+ *     y = epi(rstd_m * (x.w^T - mean_m * colsum) + bias),  mean/var over K, biased variance, rstd = 1/sqrt(var + ln_eps)
+ *     — algebraically LayerNorm(x).W^T + b.  epilogue: MVIT_EPI_NONE or MVIT_EPI_GELU.
+ */
+int mvit_linear_stat_parts(int64_t M, int N, int K);
+int mvit_linear_ln_fwd(const void *x, const void *w, const float *bias, const float *colsum, const float *ln_stats,
+                       int ln_parts, float ln_eps, const void *residual, const float *row_scale,
+                       int64_t rows_per_sample, void *y, float *stats_out, int64_t M, int N, int K, int64_t ldy,
+                       int64_t ldr, int epilogue, void *stream);
+
+/*
  * im2col for the patch-embedding Conv3d (stem_helper.py:308-338): clip [B, C, T, H, W] (channels-first,
  * as the reference feeds it) -> patch matrix [B*To*Ho*Wo, Kp] with column k = ((c*kt + a)*kh + b)*kw + d
  * (the natural flattening of the Conv3d weight [Cout, C, kt, kh, kw]); zero padding outside the clip and
@@ -215,6 +233,12 @@ int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, int B, int 
 int mvit_patch_conv_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out, int B,
                         int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t, int lo_h, int lo_w, int N,
                         void *stream);
+
+/* mvit_patch_conv_fwd that also emits the row statistics of its output tokens (producer form of mvit_linear_ln_fwd):
+ * stats_out [ceil(N/96)][B*Tf*Hf*Wf][2] fp32, indexed by token. */
+int mvit_patch_conv_stats_fwd(const void *folded, const void *wf, const float *bias, const void *pos, void *out,
+                              float *stats_out, int B, int Tf, int Hf, int Wf, int Cf, int nt, int nh, int nw, int lo_t,
+                              int lo_h, int lo_w, int N, void *stream);
 
 /* Training form of mvit_attention_pool_fwd (conv mode + LayerNorm, no cls token): additionally writes the pooled values
  * BEFORE the LayerNorm to pre_ln_out (contiguous [B, heads, L', d], dtype), which the LayerNorm backward needs — saving

@@ -251,3 +251,60 @@ def test_patch_embed_implicit_gemm_conv():
     assert rel_inf(got_clip, ref + pos) < TOL[torch.bfloat16]
     assert rel_inf(got_u8, ref + pos) < TOL[torch.bfloat16]
     assert rel_inf(got_nopos, ref) < TOL[torch.bfloat16]
+
+
+# ------------------------------------------------------------------------------------------------ folded LayerNorm
+LN_FOLD_SHAPES = [
+    # (M, K, N): block-stream widths of MViTv2-B and the three GEMM tile configurations (128x96, 128x128, CTA-pair 256x192)
+    (300, 96, 288), (1000, 96, 384), (777, 192, 576), (20000, 384, 1152), (40000, 384, 1536), (19000, 768, 2304),
+    (19000, 384, 1024), (50, 80, 40),
+]
+
+
+@pytest.mark.parametrize("M,K,N", LN_FOLD_SHAPES, ids=str)
+@pytest.mark.parametrize("gelu", [False, True], ids=["plain", "gelu"])
+def test_linear_ln_folded(M, K, N, gelu):
+    """Producer + consumer of the folded LayerNorm (mvit_linear_ln_fwd) against the oracle's LayerNorm -> Linear (-> GELU):
+    the stream x comes out of a stats-emitting GEMM (identity-ish weight + residual), so both halves are exercised."""
+    from aicity_action_b200.weights import folded_ln_linear
+    dt = torch.bfloat16
+    base = rounded(synth_input(21, f"lnf{M}{K}", (M, K)) * 1.5 + 0.7, dt)          # non-zero mean rows
+    eye = torch.eye(K) * 0.5
+    res = rounded(synth_input(22, f"lnr{M}{K}", (M, K)), dt)
+    x_dev = ops.linear_stats(dev(base, dt), dev(eye, dt), None, residual=dev(res, dt))
+    x = x_dev.float().cpu()                                                        # exactly the bf16 values the consumer reads
+    assert rel_inf(x, base @ eye.t() + res) < TOL[dt]
+    stats = ops.row_stats_of(x_dev)
+    assert stats is not None and stats.shape[1:] == (M, 2)
+    tot = stats.sum(0).cpu()
+    assert rel_inf(tot[:, 0], x.sum(1)) < 1e-4 and rel_inf(tot[:, 1], (x * x).sum(1)) < 1e-4
+    w = torch.nn.Parameter(synth_tensor(23, f"w{N}{K}", (N, K)) * K ** -0.5)
+    b = torch.nn.Parameter(synth_tensor(23, f"b{N}", (N,)) * 0.1)
+    g = torch.nn.Parameter(1.0 + 0.3 * synth_tensor(23, f"g{K}", (K,)))
+    be = torch.nn.Parameter(0.2 * synth_tensor(23, f"be{K}", (K,)))
+    ref = F.linear(F.layer_norm(x, (K,), g, be, 1e-6), w, b)
+    if gelu:
+        ref = F.gelu(ref)
+    wf, bf, cs = folded_ln_linear(w.cuda(), b.cuda(), g.cuda(), be.cuda())
+    got = ops.linear_ln(x_dev, stats, wf, bf, cs, 1e-6, gelu=gelu)
+    assert rel_inf(got, ref.detach()) < TOL[dt], rel_inf(got, ref.detach())
+    # and against the unfolded kernels on the same device values
+    xn = ops.layernorm(x_dev, g.detach().cuda(), be.detach().cuda(), 1e-6)
+    unf = ops.linear(xn, w.detach().cuda().to(dt), b.detach().cuda(), gelu=gelu)
+    assert rel_inf(got, unf) < TOL[dt]
+
+
+def test_patch_conv_row_stats():
+    """mvit_patch_conv_stats_fwd: tokens identical to mvit_patch_conv_fwd, statistics indexed by token (not by tile row)."""
+    from aicity_action_b200.mvit import PatchEmbed
+    pe = PatchEmbed(3, 96, kernel=(3, 7, 7), stride=(2, 4, 4), padding=(1, 3, 3)).cuda()
+    clip = dev(synth_input(5, "clip", (2, 3, 8, 64, 96)), torch.bfloat16)
+    pos = dev(synth_input(5, "pos", (4 * 16 * 24, 96)), torch.bfloat16)
+    a = pe(clip, torch.bfloat16, pos=pos, pos_period=pos.shape[0])
+    b = pe(clip, torch.bfloat16, pos=pos, pos_period=pos.shape[0], want_stats=True)
+    assert torch.equal(a, b)
+    st = ops.row_stats_of(b)
+    assert st is not None
+    tot = st.sum(0)
+    bf = b.float().reshape(-1, 96)
+    assert rel_inf(tot[:, 0], bf.sum(1)) < 1e-4 and rel_inf(tot[:, 1], (bf * bf).sum(1)) < 1e-4

@@ -243,3 +243,27 @@ def test_sliding_window_device_resize_equals_host_cv2_resize():
             assert (a0, a1) == (b0, b1) and (pa == pb).all()
     # the raw path uploads each distinct frame once: fewer bytes than windows x frames x raw size
     assert 0 < r_dev.h2d_bytes < 2 * 20 * cfg.DATA.NUM_FRAMES * 54 * 96 * 3
+
+
+@pytest.mark.parametrize("c", [MODEL_CASES[0], MODEL_CASES[2]], ids=lambda c: c["name"])
+def test_ln_fold_matches_unfolded_and_removes_the_layernorm_launches(c, golden, monkeypatch):
+    """Eval / bf16: norm1 and norm2 of every block are folded into the neighbouring GEMMs (MVIT_B200_LN_FOLD, default on).
+    Same fixture tolerance as the unfolded path, same arg-max, and 2 launches fewer per block."""
+    from aicity_action_b200 import ops
+    cfg = aicity_cfg(c["yaml"], tiny_cfg_overrides(c))
+    m = MViT(cfg).eval()
+    load_synth(m, c["seed"])
+    m = m.cuda()
+    x = synth_clip(c["seed"], c["B"], cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE).cuda().bfloat16()
+    ref = torch.from_numpy(golden[c["name"] + ".probs"])
+    out, launches = {}, {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MVIT_B200_LN_FOLD", flag)
+        n0 = ops.launch_count
+        with torch.no_grad():
+            out[flag] = m([x])
+        launches[flag] = ops.launch_count - n0
+        assert rel_inf(out[flag], ref) < TOL[torch.bfloat16], (flag, rel_inf(out[flag], ref))
+        assert torch.equal(out[flag].argmax(1).cpu(), ref.argmax(1))
+    assert rel_inf(out["1"], out["0"]) < TOL[torch.bfloat16]
+    assert launches["0"] - launches["1"] == 2 * len(m.blocks), launches
