@@ -46,22 +46,27 @@ template <int BN, bool PAIR> struct Cfg {
   static constexpr int kBoxes = BN / kBoxCols;
   static constexpr int kOutBytes = kBoxes * kBoxBytes;
   static constexpr int kTmemCols = BN == 192 ? 512 : 256;  // 2 accumulators of BN columns, power of two
-  // Epilogue warps: kParts per TMEM lane quarter, each owning BN / kParts columns of the tile.  The 1-CTA configurations
-  // serve the memory-bound (small-K) layers, where the epilogue IS the kernel: with two warps per scheduler it issued
-  // on 39 % of the cycles (ncu); every configuration now runs 3 (BN 96) or 4 warps per quarter.
-  static constexpr int kParts = BN == 96 ? 3 : 4;
-  static constexpr int kEpiWarps = 4 * kParts;
-  static constexpr int kEpiThreads = kEpiWarps * 32;
-  static constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 384 (pair) / 512 (BN 96) / 640 (BN 128)
-  static constexpr int kCols = BN / kParts;                // columns of one epilogue thread: 48 (BN 192) / 32
-  static constexpr int kChunk = kCols % 32 == 0 ? 32 : 16; // columns per tcgen05.ld
-  static constexpr int kNumChunks = kCols / kChunk;        // 3 / 1
-  // bias | LayerNorm column-sum slices (double-buffered) + per-part row statistics staging
-  static constexpr int kVecBytes = 4 * BN * 4;
-  static constexpr int kStatBytes = kParts * BM * 8;
+  // Epilogue: TWO independent groups of 8 warps (4 TMEM lane quarters x 2 column halves).  Group g drains accumulator g,
+  // i.e. every second tile of the CTA, with its own named barriers, bias slices, output buffers and store-issuing thread.
+  // While one group sits in a latency phase (barrier, tcgen05.ld, waiting for its TMA store to release a buffer) the other
+  // one computes: measured with ONE group of 12-16 warps in lock step the epilogue-bound layers (fc1 + GELU, the K <= 192
+  // ones) issued on only 40-50 % of the cycles, a third of them real epilogue math.
+  static constexpr int kGroups = 2;
+  static constexpr int kGroupWarps = 8;
+  static constexpr int kGroupThreads = kGroupWarps * 32;
+  static constexpr int kEpiWarps = kGroups * kGroupWarps;
+  static constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 640
+  static constexpr int kCols = BN / 2;                     // columns of one epilogue thread: 48 / 64 / 96
+  static constexpr int kBatch = BN == 128 ? 32 : 48;       // columns held in registers at a time
+  static constexpr int kBatches = kCols / kBatch;          // 1 / 2 / 2
+  static constexpr int kBufsPerGroup = kNB / kGroups;      // output buffers a group rotates through: 2 (BN 96) or 1
+  // bias | LayerNorm column-sum slices (per group, double-buffered) + per-half row statistics staging
+  static constexpr int kVecBytes = kGroups * 4 * BN * 4;
+  static constexpr int kStatBytes = kGroups * 2 * BM * 8;
   static constexpr int kLnMaxParts = 4;                    // N tiles of the producer (C <= 768 at 192 columns per tile)
-  static constexpr int kLnBytes = 2 * kLnMaxParts * BM * 8; // kLnIn: input-row statistics, double-buffered
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + kVecBytes + kStatBytes + kLnBytes + 512 + 1024;
+  static constexpr int kLnBytes = kGroups * kLnMaxParts * BM * 8;   // kLnIn: input-row statistics, one slot per group
+  // (the statistics staging of kLnStats and the statistics slots of kLnIn share their bytes: a launch runs one mode)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNB * kOutBytes + kVecBytes + (kStatBytes > kLnBytes ? kStatBytes : kLnBytes) + 512 + 1024;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory a CTA can opt into");
 };
 
@@ -168,11 +173,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint8_t *sA = smem;
   uint8_t *sB = smem + C::kStages * C::kABytes;
   uint8_t *sOut = smem + C::kStages * C::kStageBytes;
-  float *sBias = reinterpret_cast<float *>(sOut + C::kNB * C::kOutBytes);   // [2][BN] bias, then [2][BN] colsum
-  float *sCol = sBias + 2 * BN;
-  float2 *sStat = reinterpret_cast<float2 *>(sBias + 4 * BN);                // [kParts][BM]
-  float2 *sLn = sStat + C::kParts * BM;                                      // [2][kLnMaxParts][BM]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sLn + 2 * C::kLnMaxParts * BM);
+  float *sVec = reinterpret_cast<float *>(sOut + C::kNB * C::kOutBytes);    // per group: [2][BN] bias, [2][BN] colsum
+  float2 *sStatAll = reinterpret_cast<float2 *>(sVec + C::kGroups * 4 * BN); // per group: [2 halves][BM]
+  float2 *sLnAll = sStatAll;                                                 // per group: [kLnMaxParts][BM] (other mode)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStatAll + (C::kStatBytes > C::kLnBytes ? C::kStatBytes : C::kLnBytes) / 8);
   uint64_t *full = bars, *empty = full + C::kStages, *tfull = empty + C::kStages, *tempty = tfull + 2;
   uint64_t *res_full = tempty + 2, *buf_free = res_full + C::kNB;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(buf_free + C::kNB);
@@ -200,7 +204,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], PAIR ? 2 * C::kEpiWarps : C::kEpiWarps);   // PAIR: both CTAs' epilogues release the leader
+      mbar_init(&tempty[i], PAIR ? 2 * C::kGroupWarps : C::kGroupWarps);   // PAIR: both CTAs' groups release the leader
     }
     for (int i = 0; i < C::kNB; ++i) {
       mbar_init(&res_full[i], 1);
@@ -320,47 +324,55 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------ epilogue: kParts warps per TMEM lane quarter
+    // ------------------------------------------------------------ epilogue: two groups, group g drains accumulator g
     const int e = warp - kEpiWarp0;
+    const int g = e >> 3;                              // group
     const int q = e & 3;                               // TMEM lane quarter (== warp % 4)
-    const int hf = e >> 2;                             // which part of the BN columns
-    const int et = threadIdx.x - kEpiWarp0 * 32;       // 0..kEpiThreads-1
+    const int hf = (e >> 2) & 1;                       // column half of the tile
+    const int gt = threadIdx.x - (kEpiWarp0 + g * C::kGroupWarps) * 32;   // 0..255 inside the group
     const int row = q * 32 + lane;                     // row inside the tile == TMEM lane
     const uint32_t swz = (uint32_t)((row >> 1) & 3);
-    int acc = 0, buf = 0;
-    uint32_t acc_phase = 0, buf_phase = 0;
-    int64_t it = 0;
-    // bias slice of the first tile; later slices are fetched one tile ahead (global latency off the critical path)
-    TileWalk tw(tile0, tile_step, n_tiles), tw_next = tw;
+    const int bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;    // named barriers of this group
+    float *sBias = sVec + g * 4 * BN, *sCol = sBias + 2 * BN;
+    float2 *sStat = sStatAll + g * 2 * BM, *sLn = sLnAll + g * C::kLnMaxParts * BM;
+    // this group's tiles: local iterations it = g, g + 2, ... of the CTA's sequence; k counts the group's own tiles
+    const int64_t gstep = 2 * tile_step;
+    TileWalk tw(tile0 + g * tile_step, gstep, n_tiles), tw_next = tw;
     tw_next.next();
-    if (et < BN) {
-      const int n = tw.n * BN + et;
-      sBias[et] = (p.bias && tile0 < tiles && n < p.N) ? p.bias[n] : 0.f;
-      if constexpr (LNM == kLnIn) sCol[et] = (tile0 < tiles && n < p.N) ? p.colsum[n] : 0.f;
+    const int64_t t_first = tile0 + g * tile_step;
+    // bias slice of the first tile; later slices are fetched one tile ahead (global latency off the critical path)
+    if (gt < BN) {
+      const int n = tw.n * BN + gt;
+      sBias[gt] = (p.bias && t_first < tiles && n < p.N) ? p.bias[n] : 0.f;
+      if constexpr (LNM == kLnIn) sCol[gt] = (t_first < tiles && n < p.N) ? p.colsum[n] : 0.f;
     }
-    // kLnIn: (sum, sum of squares) of the 128 input rows of a tile, one slice per N tile of the producer.  Fetched one tile
-    // ahead with cp.async by the first four epilogue warps (et == row), so no thread ever waits on the L2 round trip.
-    auto fetch_row_stats = [&](int m_tile, int slot) {
-      if (et < BM) {
-        const int64_t m = min((int64_t)m_tile * TM + rank * BM + et, p.M - 1);
+    // kLnIn: (sum, sum of squares) of the 128 input rows of a tile, one slice per N tile of the producer, fetched a tile
+    // ahead with cp.async by the group's first four warps (gt == row): no thread waits on the L2 round trip
+    auto fetch_row_stats = [&](int m_tile) {
+      if (gt < BM) {
+        const int64_t m = min((int64_t)m_tile * TM + rank * BM + gt, p.M - 1);
         for (int i = 0; i < p.ln_parts; ++i)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sLn + (slot * C::kLnMaxParts + i) * BM + et)),
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sLn + i * BM + gt)),
                        "l"(p.ln_stats + (int64_t)i * p.M + m) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if constexpr (LNM == kLnIn) {
-      if (tile0 < tiles) fetch_row_stats(tw.m, 0);
+      if (t_first < tiles) fetch_row_stats(tw.m);
     }
-    for (int64_t t = tile0; t < tiles; t += tile_step, ++it, tw.next(), tw_next.next()) {
+    int k = 0;
+    for (int64_t t = t_first; t < tiles; t += gstep, ++k, tw.next(), tw_next.next()) {
+      const int it = 2 * k + g;                        // position in the CTA's tile sequence
+      const int buf = it % C::kNB;
+      const uint32_t buf_phase = (uint32_t)(it / C::kNB) & 1, acc_phase = (uint32_t)k & 1;
       const int64_t m0 = (int64_t)tw.m * TM + rank * BM;
       const int n0 = tw.n * BN;
-      const float *bias_s = sBias + (it & 1) * BN;
-      const float *col_s = sCol + (it & 1) * BN;
+      const float *bias_s = sBias + (k & 1) * BN;
+      const float *col_s = sCol + (k & 1) * BN;
       float bias_next = 0.f, col_next = 0.f;
-      const int64_t tn = t + tile_step;
-      if (et < BN && tn < tiles) {
-        const int n = tw_next.n * BN + et;
+      const int64_t tn = t + gstep;
+      if (gt < BN && tn < tiles) {
+        const int n = tw_next.n * BN + gt;
         if (n < p.N) {
           if (p.bias) bias_next = p.bias[n];
           if constexpr (LNM == kLnIn) col_next = p.colsum[n];
@@ -370,39 +382,44 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if constexpr (LNM == kLnIn) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this tile's statistics have landed
       float rs = 1.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + row, p.M - 1) / p.rows_per_sample];
-      asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");   // this tile's bias slice is visible; previous store was issued
+      // this tile's bias slice (and row statistics) are visible; the group's previous store was issued
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(C::kGroupThreads) : "memory");
       float ln_a = 1.f, ln_b = 0.f;                      // x_norm . w'^T = ln_a * acc + ln_b * colsum
       if constexpr (LNM == kLnIn) {
-        const float2 *sl = sLn + (int)(it & 1) * C::kLnMaxParts * BM + row;
-        float2 st = sl[0];
+        float2 st = sLn[row];
         for (int i = 1; i < p.ln_parts; ++i) {           // fixed order: reproducible
-          st.x += sl[i * BM].x;
-          st.y += sl[i * BM].y;
+          st.x += sLn[i * BM + row].x;
+          st.y += sLn[i * BM + row].y;
         }
-        if (tn < tiles) fetch_row_stats(tw_next.m, (int)((it + 1) & 1));   // readers of that slot passed bar.sync 1 a tile ago
         const float mean = st.x * p.ln_inv_c;
         const float var = fmaxf(st.y * p.ln_inv_c - mean * mean, 0.f);
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -mean * ln_a;
       }
       mbar_wait(&res_full[buf], buf_phase);            // buffer is ours (and holds the residual tile, if any)
-      mbar_wait(&tfull[acc], acc_phase);
+      mbar_wait(&tfull[g], acc_phase);
       tc_fence_after();
       uint8_t *obuf = sOut + buf * C::kOutBytes;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hf * C::kCols;
-      uint32_t r[C::kNumChunks][C::kChunk];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BN + hf * C::kCols;
 #pragma unroll
-      for (int c = 0; c < C::kNumChunks; ++c) {
-        if constexpr (C::kChunk == 32) tmem_ld32(taddr + c * 32, r[c]);
-        else tmem_ld16(taddr + c * 16, r[c]);
-      }
-      tmem_ld_wait();
+      for (int bt = 0; bt < C::kBatches; ++bt) {
+        uint32_t rr[C::kBatch / 16][16];
 #pragma unroll
-      for (int c = 0; c < C::kNumChunks; ++c) {
-        const int col0 = hf * C::kCols + c * C::kChunk;          // first tile column of this chunk
+        for (int c = 0; c < C::kBatch / 16; ++c) tmem_ld16(taddr + bt * C::kBatch + c * 16, rr[c]);
+        const uint32_t *r = &rr[0][0];
+        tmem_ld_wait();
+        if (bt == C::kBatches - 1) {
+          // accumulator fully read -> hand it back to the MMA warp before the math of the last batch
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_remote(&tempty[g], 0);   // the leader's MMA warp owns the accumulators
+            else mbar_arrive(&tempty[g]);
+          }
+        }
 #pragma unroll
-        for (int v = 0; v < C::kChunk / 8; ++v) {
-          const int col = col0 + v * 8;
+        for (int v = 0; v < C::kBatch / 8; ++v) {
+          const int col = hf * C::kCols + bt * C::kBatch + v * 8;   // first tile column of these 8 values
           const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + col);
           const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + col + 4);
           float2 x[4];
@@ -418,13 +435,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // register move per element
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              x[j] = make_float2(fmaf(__uint_as_float(r[c][v * 8 + 2 * j]), ln_a, sh[j].x),
-                                 fmaf(__uint_as_float(r[c][v * 8 + 2 * j + 1]), ln_a, sh[j].y));
+              x[j] = make_float2(fmaf(__uint_as_float(r[v * 8 + 2 * j]), ln_a, sh[j].x),
+                                 fmaf(__uint_as_float(r[v * 8 + 2 * j + 1]), ln_a, sh[j].y));
           } else {
-            x[0] = make_float2(__uint_as_float(r[c][v * 8 + 0]) + b0.x, __uint_as_float(r[c][v * 8 + 1]) + b0.y);
-            x[1] = make_float2(__uint_as_float(r[c][v * 8 + 2]) + b0.z, __uint_as_float(r[c][v * 8 + 3]) + b0.w);
-            x[2] = make_float2(__uint_as_float(r[c][v * 8 + 4]) + b1.x, __uint_as_float(r[c][v * 8 + 5]) + b1.y);
-            x[3] = make_float2(__uint_as_float(r[c][v * 8 + 6]) + b1.z, __uint_as_float(r[c][v * 8 + 7]) + b1.w);
+            x[0] = make_float2(__uint_as_float(r[v * 8 + 0]) + b0.x, __uint_as_float(r[v * 8 + 1]) + b0.y);
+            x[1] = make_float2(__uint_as_float(r[v * 8 + 2]) + b0.z, __uint_as_float(r[v * 8 + 3]) + b0.w);
+            x[2] = make_float2(__uint_as_float(r[v * 8 + 4]) + b1.x, __uint_as_float(r[v * 8 + 5]) + b1.y);
+            x[3] = make_float2(__uint_as_float(r[v * 8 + 6]) + b1.z, __uint_as_float(r[v * 8 + 7]) + b1.w);
           }
           if (p.epilogue == MVIT_EPI_GELU) {
 #pragma unroll
@@ -471,40 +488,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       }
       if constexpr (LNM == kLnStats) sStat[hf * BM + row] = make_float2(sum2.x + sum2.y, sq2.x + sq2.y);
-      if (et < BN) {                                             // readers of that half finished a tile ago
-        sBias[((it + 1) & 1) * BN + et] = bias_next;
-        if constexpr (LNM == kLnIn) sCol[((it + 1) & 1) * BN + et] = col_next;
+      if (gt < BN) {                                             // readers of that half finished a tile ago
+        sBias[((k + 1) & 1) * BN + gt] = bias_next;
+        if constexpr (LNM == kLnIn) sCol[((k + 1) & 1) * BN + gt] = col_next;
       }
-      // accumulator fully read -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR && rank != 0) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA warp owns the accumulators
-        else mbar_arrive(&tempty[acc]);
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      // tile is complete in shared memory -> one thread TMA-stores it
+      // tile is complete in shared memory -> one thread of the group TMA-stores it
       fence_proxy_async_smem();
-      asm volatile("bar.sync 2, %0;" ::"n"(C::kEpiThreads) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(C::kGroupThreads) : "memory");
+      if constexpr (LNM == kLnIn) {
+        if (tn < tiles) fetch_row_stats(tw_next.m);              // every thread of the group has read the slot (bar_b)
+      }
       if constexpr (LNM == kLnStats) {
-        if (et < BM) {                                           // et == row for the first four epilogue warps
-          float2 tot = sStat[et];
-#pragma unroll
-          for (int i = 1; i < C::kParts; ++i) {
-            const float2 v = sStat[i * BM + et];
-            tot.x += v.x;
-            tot.y += v.y;
-          }
-          int64_t token = m0 + et;
+        if (gt < BM) {                                           // gt == row for the first four warps of the group
+          const float2 v0 = sStat[gt], v1 = sStat[BM + gt];
+          const float2 tot = make_float2(v0.x + v1.x, v0.y + v1.y);
+          int64_t token = m0 + gt;
           if (p.conv.enabled) {                                  // tile row -> token of the 8(w) x 8(h) x 2(t) patch
             const TileCoord tc = conv_tile(p.conv, tw.m);
-            token = (((int64_t)tc.b * p.conv.Tf + tc.t0 + (et >> 6)) * p.conv.Hf + tc.h0 + ((et >> 3) & 7)) * p.conv.Wf +
-                    tc.w0 + (et & 7);
+            token = (((int64_t)tc.b * p.conv.Tf + tc.t0 + (gt >> 6)) * p.conv.Hf + tc.h0 + ((gt >> 3) & 7)) * p.conv.Wf +
+                    tc.w0 + (gt & 7);
           }
           if (token < p.M) p.stats_out[(int64_t)tw.n * p.M + token] = tot;
         }
       }
-      if (et == 0) {
+      if (gt == 0) {
         if (p.conv.enabled) {
           const TileCoord tc = conv_tile(p.conv, tw.m);
 #pragma unroll
@@ -517,14 +524,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (n0 + bx * kBoxCols < p.N) tma_store_2d(&tmap_y, obuf + bx * kBoxBytes, n0 + bx * kBoxCols, (int)m0);
         }
         tma_store_commit();
-        if (it > 0) {
-          tma_store_wait_read<1>();                    // the previous tile's store has drained its buffer
-          mbar_arrive(&buf_free[(buf + C::kNB - 1) % C::kNB]);
+        // the group keeps kBufsPerGroup - 1 stores in flight; the older one has drained its buffer -> hand it back
+        if (k >= C::kBufsPerGroup - 1) {
+          tma_store_wait_read<C::kBufsPerGroup - 1>();
+          mbar_arrive(&buf_free[(it - 2 * (C::kBufsPerGroup - 1)) % C::kNB]);
         }
       }
-      if (++buf == C::kNB) { buf = 0; buf_phase ^= 1; }
     }
-    if (et == 0) tma_store_wait_all<0>();              // global writes complete before the CTA retires
+    if (gt == 0) tma_store_wait_all<0>();              // global writes complete before the CTA retires
   }
   tc_fence_before();
   if constexpr (PAIR) {
