@@ -1,8 +1,8 @@
 // attention_pool for the shipped MViTv2 configuration, bf16: the three depthwise 3x3x3 Conv3d poolings of Q, K and V
 // (stride (1,s,s), pad 1, head_dim 96) fused with their LayerNorms, reading the qkv GEMM output [B, N, 3, heads, 96]
 // in place (attention.py:172-212 pool_{q,k,v} + attention.py:66-67 norm_{q,k,v}).  HBM-bound overall;
-// the stride-1 pools are co-limited by the fp32 FMA pipe (27 FMA per output element), so the design goal is to issue
-// nothing but the FMAs: everything that was address arithmetic or copy issue in pool_tiled.cu is gone.
+// the stride-1 pools are co-limited by the fp32 FMA pipe (27 FMA per output element), so the design goal is that the
+// warps which own the FMA pipe issue (almost) nothing but FMAs.
 //
 //  * PERSISTENT CTAs (two per SM) walk a static round-robin list of work items = (q|k|v, batch*head, 4x8 or 2x8 output
 //    tile, frame range); q, k and v of equal stride share ONE launch (blockIdx.y picks the tensor, so the 81 filter taps a
@@ -10,16 +10,22 @@
 //  * A PRODUCER WARP feeds a ring of halo tiles with one 5-D TMA load per input frame (tensor map over the qkv tensor:
 //    [channel, w, h, t, b]; the out-of-image halo is zero-filled by the TMA unit = the conv's zero padding), completion on
 //    full/empty mbarriers — no per-thread cp.async issue, no offset table, no __syncthreads in the frame loop.
-//  * FOUR CONSUMER WARPS (warpgroup 0): a warp owns CPW consecutive output columns of one output row.  Every lane owns
+//  * FOUR CONVOLUTION WARPS (warpgroup 0): a warp owns CPW consecutive output columns of one output row.  Every lane owns
 //    the channel pair {2L, 2L+1} of all CPW columns, and the channel pair {64+2(L%16), 65+2(L%16)} of the half of the
 //    columns its half-warp is responsible for — so ALL multiply-adds are packed fp32x2 FMAs on natural channel pairs
 //    (bit-identical to two fmaf), 324 per warp and frame, with no register shuffling to form pairs.  An input frame t feeds
 //    output frames t-1, t, t+1 through three rolling accumulator sets; the frame loop is unrolled by three so the rotation
-//    is a renaming, not register moves.  The LayerNorm runs, also in packed arithmetic, on a per-warp fp32 staging tile
-//    that turns the conv layout into "4 (8) lanes per column x 24 (12) contiguous channels".
-//  * REGISTERS: the CTA is two warpgroups launched at 128 registers per thread (two CTAs per SM); the producer warpgroup
-//    gives registers back (setmaxnreg.dec 40) and the consumer warpgroup takes them (setmaxnreg.inc 216): the 54 filter
-//    taps + 72 accumulators + a row of inputs live in registers without spills at full occupancy.
+//    is a renaming, not register moves.  A finished output frame leaves the warp as fp32 through a double-buffered staging
+//    tile in shared memory (12 stores per lane + one mbarrier arrive; three tiles per warp) — the convolution warps never run the LayerNorm.
+//  * THREE LAYERNORM WARPS (the producer's warpgroup) drain the staging tiles round-robin: 4 (8) lanes per column, 24 (12)
+//    channels per lane, one sweep for sum and sum of squares, packed arithmetic, bf16 rows stored straight to
+//    [B, heads, L', 96].  ncu on the previous
+//    version (LayerNorm inside the convolution warps) showed them spending as many stall samples in the latency-bound
+//    LayerNorm / store tail as in the convolution, with the FMA pipe 44 % busy; now the tail overlaps the FMAs of all
+//    four convolution warps.
+//  * REGISTERS: the CTA is two warpgroups launched at 128 registers per thread (two CTAs per SM); the producer / LayerNorm
+//    warpgroup gives registers back (setmaxnreg.dec 80) and the convolution warpgroup takes them (setmaxnreg.inc 176): the
+//    54 filter taps + 72 accumulators + a row of inputs live in registers without spills at full occupancy.
 #include <algorithm>
 #include <type_traits>
 
@@ -31,21 +37,26 @@ namespace ptma {
 
 using namespace tc;
 
-constexpr int kConsumerWarps = 4;
-constexpr int kThreads = 256;      // warpgroup 0: consumers; warpgroup 1: warp 4 = TMA producer, warps 5-7 only donate registers
+constexpr int kConvWarps = 4;
+constexpr int kLnWarps = 3;        // warps 5-7; warp 4 is the TMA producer
+constexpr int kStgBufs = 3;        // staging tiles per convolution warp: emit n uses tile n % 3, which makes LayerNorm warp
+                                   // (n + w) % 3 the ONLY consumer of tile (w, n % 3) — a waiter that could run two phases
+                                   // ahead of an mbarrier would see its parity test pass falsely
+constexpr int kThreads = 256;
 constexpr int TW = 8;
-constexpr int kStgPitch = 100;   // floats per staged column (96 + 4 pad: conflict-free 16-byte reads)
+constexpr int kStgPitch = 100;   // floats per staged column (96 + 4 pad)
 constexpr int kPitch = 192;      // bytes per position (96 bf16)
 
 template <int S> struct Geo {
   static constexpr int CPW = S == 1 ? 8 : 4;                            // output columns per warp
-  static constexpr int TH = S == 1 ? kConsumerWarps : kConsumerWarps / 2;   // one warp per row, or two warps per row
+  static constexpr int TH = S == 1 ? kConvWarps : kConvWarps / 2;       // one warp per row, or two warps per row
   static constexpr int NR = (TH - 1) * S + 3;                           // input rows / cols of the halo tile
   static constexpr int NC = (TW - 1) * S + 3;
   static constexpr int WC = (CPW - 1) * S + 3;                          // input cols one warp touches
   static constexpr int kFrameBytes = NR * NC * kPitch;
   static constexpr int kStageBytes = (kFrameBytes + 127) & ~127;        // TMA destinations stay 128-byte aligned
-  static constexpr int kStages = S == 1 ? 8 : 5;
+  static constexpr int kStages = S == 1 ? 6 : 5;
+  static constexpr int kStgFloats = CPW * kStgPitch;                    // one staging tile
 };
 
 struct Stream {              // one of q / k / v
@@ -58,12 +69,29 @@ struct Params {
   int heads, T, To, Ho, Wo, tiles_h, tiles_w, t_per_item, t_splits, items;
   float eps;
 };
+struct StgMeta {             // where a staged tile goes: written by the convolution warp, read by the LayerNorm warp
+  long long off;             // element offset of (column 0, channel 0) in out / pre
+  int ncols, pad;            // live columns (0: nothing to store — halo frame of a split item, or a row below the image)
+};
 
-__device__ __forceinline__ void load3(const uint8_t *pos, int lane, float2 &xy, float &z) {
-  const uint32_t u = *reinterpret_cast<const uint32_t *>(pos + 4 * lane);
-  xy.x = __uint_as_float(u << 16);
-  xy.y = __uint_as_float(u & 0xffff0000u);
-  z = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(pos + 128 + 2 * lane)) << 16);
+
+// mbarrier operations on a raw shared-window address: the convolution warps keep their barrier addresses in registers
+// (re-deriving them from generic pointers cost ~40 dependent instructions per frame, S2R / S2UR reads included)
+__device__ __forceinline__ void bar_wait(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait(addr, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(addr, parity)) {
+    if ((++spins & 1023u) == 0) {
+      if (*reinterpret_cast<volatile unsigned int *>(&g_tc_fault) != 0) return;
+      if (spins > (1u << 26)) {
+        atomicExch(&g_tc_fault, 1u);
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void bar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 
 template <int S>
@@ -75,16 +103,23 @@ pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t *stages = smem;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + G::kStages * G::kStageBytes);
   uint64_t *empty = full + G::kStages;
-  float *gb_s = reinterpret_cast<float *>(empty + G::kStages);          // gamma[96] | beta[96]
+  uint64_t *stg_full = empty + G::kStages;                              // [conv warp][kStgBufs]
+  uint64_t *stg_empty = stg_full + kStgBufs * kConvWarps;
+  StgMeta *meta = reinterpret_cast<StgMeta *>(stg_empty + kStgBufs * kConvWarps);   // [conv warp][kStgBufs]
+  float *gb_s = reinterpret_cast<float *>(meta + kStgBufs * kConvWarps);   // gamma[96] | beta[96]
   float2 *wz_s = reinterpret_cast<float2 *>(gb_s + 192);                // [27 taps][16 channel pairs of 64..95]
-  float *stg_all = reinterpret_cast<float *>(wz_s + 27 * 16);
+  float *stg_all = reinterpret_cast<float *>(wz_s + 27 * 16);           // [conv warp][kStgBufs][CPW][kStgPitch]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Stream &sm = p.s[blockIdx.y];
   if (threadIdx.x == 0) {
     for (int i = 0; i < G::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kConsumerWarps);
+      mbar_init(&empty[i], kConvWarps);
+    }
+    for (int i = 0; i < kStgBufs * kConvWarps; ++i) {
+      mbar_init(&stg_full[i], 1);
+      mbar_init(&stg_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -109,33 +144,127 @@ pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     to0 = ts * p.t_per_item;
     to1 = min(to0 + p.t_per_item, p.To);
   };
+  // frames an item reads / steps it takes: one step per input frame, plus a flush step after the last frame of the clip
+  auto frame_range = [&](int to0, int to1, int &t_first, int &t_last, int &t_end) {
+    t_first = max(to0 - 1, 0);
+    t_last = min(to1, p.T - 1);
+    t_end = t_last + (to1 == p.T ? 1 : 0);
+  };
 
-  if (warp >= kConsumerWarps) {
-    // ------------------------------------------------------------------ producer warpgroup: hand registers to the consumers
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == kConsumerWarps && lane == 0) {                          // one lane issues every TMA load
-      tma_prefetch_desc(&tmap);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int bh, tile_h, tile_w, to0, to1;
-        decode(item, bh, tile_h, tile_w, to0, to1);
-        const int b = bh / p.heads, head = bh - b * p.heads;
-        const int t_first = max(to0 - 1, 0), t_last = min(to1, p.T - 1);
-        const int h0 = tile_h * G::TH * S - 1, w0 = tile_w * TW * S - 1;
-        for (int t = t_first; t <= t_last; ++t, ++it) {
-          const uint32_t slot = it % G::kStages, ph = (it / G::kStages) & 1;
-          mbar_wait(&empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&full[slot], G::kFrameBytes);
-          tma_load_5d(stages + slot * G::kStageBytes, &tmap, &full[slot], sm.c0 + head * 96, w0, h0, t, b);
+  if (warp >= kConvWarps) {
+    // ------------------------------------------------------------------ producer / LayerNorm warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp == kConvWarps) {
+      if (lane == 0) {                                                  // one lane issues every TMA load
+        tma_prefetch_desc(&tmap);
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+          int bh, tile_h, tile_w, to0, to1, t_first, t_last, t_end;
+          decode(item, bh, tile_h, tile_w, to0, to1);
+          frame_range(to0, to1, t_first, t_last, t_end);
+          const int b = bh / p.heads, head = bh - b * p.heads;
+          const int h0 = tile_h * G::TH * S - 1, w0 = tile_w * TW * S - 1;
+          for (int t = t_first; t <= t_last; ++t, ++it) {
+            const uint32_t slot = it % G::kStages, ph = (it / G::kStages) & 1;
+            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&full[slot], G::kFrameBytes);
+            tma_load_5d(stages + slot * G::kStageBytes, &tmap, &full[slot], sm.c0 + head * 96, w0, h0, t, b);
+          }
         }
+      }
+      return;
+    }
+    // ---- LayerNorm warps: staged tiles are numbered idx = 4 * n + w (n-th emit of convolution warp w); warp l takes
+    // idx = l, l + 3, ... in increasing order (every wait is for a tile older than anything that could wait on us)
+    const int l = warp - kConvWarps - 1;
+    constexpr int LPC = 32 / CPW;                                       // lanes per column: 4 (stride 1) or 8
+    constexpr int CH = 96 / LPC;                                        // channels per lane: 24 or 12
+    const int jc = lane / LPC, part = lane % LPC;                       // column of the tile, channel slice
+    uint32_t n = 0;                                                     // emits per convolution warp so far
+    uint32_t kb = 0, kph = 0;                                           // n % 3 and (n / 3) & 1
+    int next = l;                                                       // next idx of this warp, relative to 4 * n
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int bh, tile_h, tile_w, to0, to1, t_first, t_last, t_end;
+      decode(item, bh, tile_h, tile_w, to0, to1);
+      frame_range(to0, to1, t_first, t_last, t_end);
+      for (int t = t_first; t <= t_end; ++t, ++n) {
+        for (; next < kConvWarps; next += kLnWarps) {
+          const int w = next;
+          const uint32_t bsel = kb;
+          mbar_wait(&stg_full[w * kStgBufs + bsel], kph);
+          const StgMeta m = meta[w * kStgBufs + bsel];
+          if (m.ncols > 0) {                                            // warp-uniform
+            const float *src = stg_all + (w * kStgBufs + bsel) * G::kStgFloats + jc * kStgPitch + part * CH;
+            float2 x[CH / 2];
+#pragma unroll
+            for (int k = 0; k < CH / 4; ++k) {
+              const float4 v = *reinterpret_cast<const float4 *>(src + 4 * k);
+              x[2 * k] = make_float2(v.x, v.y);
+              x[2 * k + 1] = make_float2(v.z, v.w);
+            }
+            const bool live = jc < m.ncols;
+            auto store_row = [&](bf16 *base) {
+              uint32_t wd[CH / 2];
+#pragma unroll
+              for (int k = 0; k < CH / 2; ++k) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(x[k].x, x[k].y);
+                wd[k] = *reinterpret_cast<const uint32_t *>(&h);
+              }
+              bf16 *row = base + m.off + jc * 96 + part * CH;
+              if constexpr (CH == 24) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                  *reinterpret_cast<uint4 *>(row + 8 * k) = make_uint4(wd[4 * k], wd[4 * k + 1], wd[4 * k + 2], wd[4 * k + 3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2 *>(row + 4 * k) = make_uint2(wd[2 * k], wd[2 * k + 1]);
+              }
+            };
+            if (sm.pre != nullptr && live) store_row(sm.pre);           // training: keep the conv output for the LN backward
+            if (sm.gamma != nullptr) {
+              // one sweep: sum and sum of squares on independent accumulators, reduced together (fp32; the variance of 96
+              // O(1) values loses nothing to the E[x^2] - mean^2 form), then y = x * (rstd*gamma) + (beta - mean*rstd*gamma)
+              float2 sa = x[0], sb = x[1], qa = __fmul2_rn(x[0], x[0]), qb = __fmul2_rn(x[1], x[1]);
+#pragma unroll
+              for (int k = 2; k < CH / 2; k += 2) {
+                sa = __fadd2_rn(sa, x[k]);
+                sb = __fadd2_rn(sb, x[k + 1]);
+                qa = __ffma2_rn(x[k], x[k], qa);
+                qb = __ffma2_rn(x[k + 1], x[k + 1], qb);
+              }
+              const float2 s2 = __fadd2_rn(sa, sb), q2 = __fadd2_rn(qa, qb);
+              float sum = s2.x + s2.y, ss = q2.x + q2.y;
+#pragma unroll
+              for (int o = LPC / 2; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+              }
+              const float mean = sum * (1.0f / 96.0f);
+              const float rstd = rsqrtf(fmaxf(ss * (1.0f / 96.0f) - mean * mean, 0.f) + p.eps);
+              const float2 r2 = make_float2(rstd, rstd), nm = make_float2(-mean * rstd, -mean * rstd);
+#pragma unroll
+              for (int k = 0; k < CH / 4; ++k) {
+                const float4 g = *reinterpret_cast<const float4 *>(gb_s + part * CH + 4 * k);
+                const float4 bt = *reinterpret_cast<const float4 *>(gb_s + 96 + part * CH + 4 * k);
+                const float2 g0 = make_float2(g.x, g.y), g1 = make_float2(g.z, g.w);
+                x[2 * k] = __ffma2_rn(x[2 * k], __fmul2_rn(r2, g0), __ffma2_rn(nm, g0, make_float2(bt.x, bt.y)));
+                x[2 * k + 1] = __ffma2_rn(x[2 * k + 1], __fmul2_rn(r2, g1), __ffma2_rn(nm, g1, make_float2(bt.z, bt.w)));
+              }
+            }
+            if (live) store_row(sm.out);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stg_empty[w * kStgBufs + bsel]);  // the convolution warp may refill the tile
+        }
+        next -= kConvWarps;
+        if (++kb == kStgBufs) { kb = 0; kph ^= 1; }
       }
     }
     return;
   }
 
-  // -------------------------------------------------------------------- consumer warpgroup
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-  float *stg = stg_all + warp * (CPW * kStgPitch);
+  // -------------------------------------------------------------------- convolution warpgroup
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
   // filter taps of the channel pair {2L, 2L+1} in registers; those of the second pair come from shared memory (wz_s)
   float2 wxy[27];
 #pragma unroll
@@ -151,7 +280,15 @@ pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   float2 axy[3][CPW];
   float2 az2[3][ZC];
 
-  int bh = 0, ho0 = 0, wo0 = 0, to0 = 0, to1 = 0;
+  int to0 = 0, to1 = 0;
+  // control state kept incremental (no divisions, no address re-derivation in the frame loop)
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+  const uint32_t stgf0 = smem_u32(stg_full) + warp * kStgBufs * 8, stge0 = smem_u32(stg_empty) + warp * kStgBufs * 8;
+  uint32_t slot = 0, slot_ph = 0;                      // TMA ring position
+  uint32_t e_buf = 0, e_ph = 0;                        // staging tile of the next emit: count % 3, (count / 3) & 1
+  long long out_off = 0;                               // element offset of this warp's first column in the frame being emitted
+  int row_cols = 0;                                    // live columns of this warp's row (0 below the image)
+  const long long frame_elems = (long long)p.Ho * p.Wo * 96;
 
   // accumulate input frame `buf` into the three output frames it touches: tap kt of output frame t + 1 - kt lives in
   // accumulator set (R + 2 - kt) % 3
@@ -189,118 +326,58 @@ pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     }
   };
 
-  // LayerNorm + store of output frame `to` held in accumulator set A, then clear the set
+  // hand output frame `to` (accumulator set A) to the LayerNorm warps, then clear the set.  Straight-line on purpose:
+  // frames outside [to0, to1) (the halo frame of a split item) are staged too, with ncols = 0 — a branch here costs
+  // register shuffles at the merge in the unrolled loop, and the emit count stays in step with the LayerNorm warps'.
   auto emit = [&](int to, auto Ac) {
     constexpr int A = decltype(Ac)::value;
-    {
-      // straight-line on purpose: frames outside [to0, to1) (the halo frame of a split item) run the arithmetic too and
-      // only their stores are predicated off — a branch here costs register shuffles at the merge in the unrolled loop
+    bar_wait(stge0 + e_buf * 8, e_ph ^ 1);                              // the tile's previous contents (3 emits ago) are drained
+    float *stg = stg_all + (warp * kStgBufs + e_buf) * G::kStgFloats;
 #pragma unroll
-      for (int j = 0; j < CPW; ++j) *reinterpret_cast<float2 *>(stg + j * kStgPitch + 2 * lane) = axy[A][j];
+    for (int j = 0; j < CPW; ++j) *reinterpret_cast<float2 *>(stg + j * kStgPitch + 2 * lane) = axy[A][j];
 #pragma unroll
-      for (int j = 0; j < ZC; ++j) *reinterpret_cast<float2 *>(stg + (jz0 + j) * kStgPitch + 64 + 2 * zl) = az2[A][j];
-      __syncwarp();
-      constexpr int LPC = 32 / CPW;            // lanes per column: 4 or 8
-      constexpr int CH = 96 / LPC;             // channels per lane: 24 or 12
-      const int jc = lane / LPC, part = lane % LPC;
-      float2 x[CH / 2];
-#pragma unroll
-      for (int k = 0; k < CH / 4; ++k) {
-        const float4 v = *reinterpret_cast<const float4 *>(stg + jc * kStgPitch + part * CH + 4 * k);
-        x[2 * k] = make_float2(v.x, v.y);
-        x[2 * k + 1] = make_float2(v.z, v.w);
-      }
-      const int ho = ho0 + hl, wo = wo0 + cl0 + jc;
-      const bool inside = ho < p.Ho && wo < p.Wo && to >= to0 && to < to1;
-      const int64_t row_off = (((int64_t)bh * p.To + to) * p.Ho * p.Wo + (int64_t)ho * p.Wo + wo) * 96 + part * CH;
-      auto store_row = [&](bf16 *base) {
-        uint32_t wd[CH / 2];
-#pragma unroll
-        for (int k = 0; k < CH / 2; ++k) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(x[k].x, x[k].y);
-          wd[k] = *reinterpret_cast<const uint32_t *>(&h);
-        }
-        bf16 *row = base + row_off;
-        if constexpr (CH == 24) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            *reinterpret_cast<uint4 *>(row + 8 * k) = make_uint4(wd[4 * k], wd[4 * k + 1], wd[4 * k + 2], wd[4 * k + 3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2 *>(row + 4 * k) = make_uint2(wd[2 * k], wd[2 * k + 1]);
-        }
-      };
-      if (sm.pre != nullptr && inside) store_row(sm.pre);      // training: keep the conv output for the LayerNorm backward
-      if (sm.gamma != nullptr) {
-        // four independent partial sums (a serial chain of 12 dependent adds would expose 12 x 4 cycles of latency)
-        float2 sa = x[0], sb = x[1], sc = x[2], sd = x[3];
-#pragma unroll
-        for (int k = 4; k < CH / 2; ++k) {
-          if (k % 4 == 0) sa = __fadd2_rn(sa, x[k]);
-          else if (k % 4 == 1) sb = __fadd2_rn(sb, x[k]);
-          else if (k % 4 == 2) sc = __fadd2_rn(sc, x[k]);
-          else sd = __fadd2_rn(sd, x[k]);
-        }
-        sa = __fadd2_rn(sa, sc);
-        sb = __fadd2_rn(sb, sd);
-        const float2 s2 = __fadd2_rn(sa, sb);
-        float sum = s2.x + s2.y;
-#pragma unroll
-        for (int o = LPC / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * (1.0f / 96.0f);
-        const float2 nm = make_float2(-mean, -mean);
-        float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < CH / 2; k += 2) {
-          x[k] = __fadd2_rn(x[k], nm);
-          x[k + 1] = __fadd2_rn(x[k + 1], nm);
-          qa = __ffma2_rn(x[k], x[k], qa);
-          qb = __ffma2_rn(x[k + 1], x[k + 1], qb);
-        }
-        const float2 q2 = __fadd2_rn(qa, qb);
-        float ss = q2.x + q2.y;
-#pragma unroll
-        for (int o = LPC / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float rstd = rsqrtf(ss * (1.0f / 96.0f) + p.eps);
-        const float2 r2 = make_float2(rstd, rstd);
-#pragma unroll
-        for (int k = 0; k < CH / 4; ++k) {
-          const float4 g = *reinterpret_cast<const float4 *>(gb_s + part * CH + 4 * k);
-          const float4 bt = *reinterpret_cast<const float4 *>(gb_s + 96 + part * CH + 4 * k);
-          x[2 * k] = __ffma2_rn(__fmul2_rn(x[2 * k], r2), make_float2(g.x, g.y), make_float2(bt.x, bt.y));
-          x[2 * k + 1] = __ffma2_rn(__fmul2_rn(x[2 * k + 1], r2), make_float2(g.z, g.w), make_float2(bt.z, bt.w));
-        }
-      }
-      if (inside) store_row(sm.out);
-      __syncwarp();   // staging is rewritten by the next emit
+    for (int j = 0; j < ZC; ++j) *reinterpret_cast<float2 *>(stg + (jz0 + j) * kStgPitch + 64 + 2 * zl) = az2[A][j];
+    if (lane == 0) {
+      StgMeta m;
+      m.off = out_off;
+      m.ncols = (to >= to0 && to < to1) ? row_cols : 0;
+      m.pad = 0;
+      meta[warp * kStgBufs + e_buf] = m;
     }
+    out_off += frame_elems;
+    __syncwarp();
+    if (lane == 0) bar_arrive(stgf0 + e_buf * 8);
+    if (++e_buf == kStgBufs) { e_buf = 0; e_ph ^= 1; }
 #pragma unroll
     for (int j = 0; j < CPW; ++j) axy[A][j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < ZC; ++j) az2[A][j] = make_float2(0.f, 0.f);
   };
 
-  uint32_t it = 0;
   // one step: input frame t (if there is one) is accumulated, then output frame t-1 is complete.  R = (t - t_first) % 3
   // names the accumulator set that holds output frame t-1.
   auto step = [&](int t, int t_last, auto Rc) {
     constexpr int R = decltype(Rc)::value;
     if (t <= t_last) {
-      const uint32_t slot = it % G::kStages, ph = (it / G::kStages) & 1;
-      ++it;
-      mbar_wait(&full[slot], ph);
+      bar_wait(full0 + slot * 8, slot_ph);
       accumulate(stages + slot * G::kStageBytes, Rc);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);          // this warp is done reading the halo tile
+      if (lane == 0) bar_arrive(empty0 + slot * 8);      // this warp is done reading the halo tile
+      if (++slot == G::kStages) { slot = 0; slot_ph ^= 1; }
     }
     emit(t - 1, std::integral_constant<int, R>{});
   };
 
   for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-    int tile_h, tile_w;
+    int bh, tile_h, tile_w, t_first, t_last, t_end;
     decode(item, bh, tile_h, tile_w, to0, to1);
-    ho0 = tile_h * G::TH;
-    wo0 = tile_w * TW;
+    frame_range(to0, to1, t_first, t_last, t_end);
+    {
+      const int ho = tile_h * G::TH + hl, wo = tile_w * TW + cl0;
+      row_cols = ho < p.Ho ? max(0, min(CPW, p.Wo - wo)) : 0;
+      // the first emit of an item is output frame t_first - 1
+      out_off = (((long long)bh * p.To + (t_first - 1)) * p.Ho * p.Wo + (long long)ho * p.Wo + wo) * 96;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -308,9 +385,6 @@ pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 #pragma unroll
       for (int j = 0; j < ZC; ++j) az2[k][j] = make_float2(0.f, 0.f);
     }
-    const int t_first = max(to0 - 1, 0), t_last = min(to1, p.T - 1);
-    // the last frame of the clip has no successor to complete it: one extra emit-only step flushes output frame T-1
-    const int t_end = t_last + (to1 == p.T ? 1 : 0);
     int t = t_first;
     while (true) {
       step(t, t_last, std::integral_constant<int, 0>{});
@@ -355,8 +429,9 @@ static int launch(const void *qkv, int B, int heads, int T, int H, int W, const 
   const uint32_t box[5] = {96, (uint32_t)G::NC, (uint32_t)G::NR, 1, 1};
   int r = encode_tmap_bf16(&tmap, qkv, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (r) return r;
-  const size_t smem = (size_t)G::kStages * G::kStageBytes + 2 * G::kStages * sizeof(uint64_t) +
-                      (192 + 27 * 16 * 2 + kConsumerWarps * G::CPW * kStgPitch) * sizeof(float);
+  const size_t smem = (size_t)G::kStages * G::kStageBytes + (2 * G::kStages + 2 * kStgBufs * kConvWarps) * sizeof(uint64_t) +
+                      kStgBufs * kConvWarps * sizeof(StgMeta) +
+                      (192 + 27 * 16 * 2 + kConvWarps * kStgBufs * G::kStgFloats) * sizeof(float);
   MVIT_SMEM_OPT_IN(pool_tma_kernel<S>, smem);
   dim3 grid((unsigned)std::min<int64_t>(items, ctas_per_stream), (unsigned)n_streams);
   pool_tma_kernel<S><<<grid, kThreads, smem, st>>>(tmap, p);
@@ -424,3 +499,4 @@ extern "C" int mvit_attention_pool_qkv_fwd(const void *qkv, int B, int heads, in
   }
   return 0;
 }
+
