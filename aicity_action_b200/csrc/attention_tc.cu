@@ -17,6 +17,8 @@
 //               warps normalise O, add the pooled-q residual and store [B, Lq, heads*96] directly.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "attention.cuh"
 #include "tc_common.cuh"
 
@@ -35,12 +37,20 @@ constexpr int kKTileBytes = kChunks * kKChunkBytes;  // 12 KB
 // tensor core multiplies, so no row-sum arithmetic is left in the softmax warps.
 constexpr int kVTileBytes = (kChunks + 1) * kKChunkBytes;   // 16 KB
 constexpr int kStageBytes = kKTileBytes + kVTileBytes;      // 28 KB
-constexpr int kStages = 6;
-constexpr int kThreads = 384;
-constexpr int kSmemBytes = 2 * kQTileBytes + kStages * kStageBytes + 512 + 1024;
-constexpr uint32_t kTmemCols = 512;
+// Two launch shapes.  NS = 2: one CTA per SM, 256 query rows as two streams sharing every K/V tile, 6-stage ring, all of
+// TMEM.  NS = 1: a 128-row single-stream CTA sized so that TWO are resident per SM (3-stage ring, 256 TMEM columns, 8
+// warps) — each loads its own K/V, but prologue / epilogue / pipeline ramp of one CTA overlap the steady state of the
+// other, which pays when a CTA lives for only ~25 key tiles (Lk = 1568: the fixed cost was ~8 of ~28 us).
+template <int NS> struct Shape {
+  static constexpr int kStages = NS == 2 ? 6 : 3;
+  static constexpr int kThreads = NS == 2 ? 384 : 256;
+  static constexpr int kSmemBytes = NS * kQTileBytes + kStages * kStageBytes + 512 + 1024;
+  static constexpr uint32_t kTmemCols = NS == 2 ? 512 : 256;
+  static constexpr uint32_t kColO = NS * 128;        // S[i][b] at 128*i + 64*b, O_i at kColO + 112*i
+  static constexpr int kCtasPerSm = NS == 2 ? 1 : 2;
+};
 constexpr int DO = D + 16;                           // accumulator columns per stream: 96 outputs + denominator (+pad)
-constexpr uint32_t kColS = 0, kColO = 256;           // S[i][b] at 128*i + 64*b, O_i at 256 + 112*i
+constexpr uint32_t kColS = 0;
 constexpr float kRescaleThreshold = 8.0f;            // log2 units
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, no range fix-ups
@@ -80,30 +90,33 @@ struct Params {
 };
 
 // POLY: how many of every 4 score pairs take the FMA-pipe exp2 (0 = all MUFU, 1 = 25 %, 2 = 50 %)
-template <int POLY>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int POLY, int NS>
+__global__ void __launch_bounds__(Shape<NS>::kThreads, Shape<NS>::kCtasPerSm)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
   // to LDS / STS instead of generic LD / ST
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t *sQ = smem;                                  // [2][24 KB]
-  uint8_t *sKV = smem + 2 * kQTileBytes;               // [stage][K 12 KB | V 12 KB]
+  constexpr int kStages = Shape<NS>::kStages, kThreads = Shape<NS>::kThreads;
+  constexpr uint32_t kTmemCols = Shape<NS>::kTmemCols, kColO = Shape<NS>::kColO;
+  uint8_t *sQ = smem;                                  // [NS][24 KB]
+  uint8_t *sKV = smem + NS * kQTileBytes;              // [stage][K 12 KB | V 12 KB]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * kStageBytes);
   uint64_t *q_full = bars;                 // 1
   uint64_t *k_full = bars + 1;             // kStages
   uint64_t *v_full = k_full + kStages;     // kStages
-  uint64_t *kv_empty = v_full + kStages;   // kStages
-  uint64_t *s_full = kv_empty + kStages;   // [stream][buffer]
+  uint64_t *k_empty = v_full + kStages;    // kStages: K(j) is free once QK(j) has run, two tiles before V(j) is
+  uint64_t *v_empty = k_empty + kStages;   // kStages
+  uint64_t *s_full = v_empty + kStages;    // [stream][buffer]
   uint64_t *p_ready = s_full + 4;          // [stream][buffer]
   uint64_t *o_done = p_ready + 4;          // [stream]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * BQ);
-  const bool two = q0 + BQ < p.Lq;                     // second 128-row tile has at least one live row
+  const int q0 = blockIdx.x * (NS * BQ);
+  const bool two = NS == 2 && q0 + BQ < p.Lq;          // second 128-row tile has at least one live row
   const int nkv = (p.Lk + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
@@ -116,7 +129,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], two ? 2 : 1);   // one tcgen05.commit per active stream
+      mbar_init(&k_empty[i], two ? 2 : 1);    // one tcgen05.commit per active stream
+      mbar_init(&v_empty[i], two ? 2 : 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -148,7 +162,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if constexpr (NS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // -------------------------------------------------------------- TMA producer
       const int ntile = two ? 2 : 1;
@@ -156,14 +171,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int i = 0; i < ntile; ++i)
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(sQ + i * kQTileBytes + c * kQChunkBytes, &tmap_q, q_full, c * kChunkCols, q0 + i * BQ, bh);
+      // K ring: a stage is released by the commit that follows QK(j), so K(j+2), K(j+3) stream in while tile j is still
+      // in its softmax / PV phase (with K and V released together a 3-stage ring left no slack for the load latency)
       for (int j = 0; j < nkv; ++j) {
         const int s = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t *kdst = sKV + s * kStageBytes, *vdst = kdst + kKTileBytes;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        uint8_t *kdst = sKV + s * kStageBytes;
         mbar_arrive_expect_tx(&k_full[s], kKTileBytes);
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(kdst + c * kKChunkBytes, &tmap_k, &k_full[s], c * kChunkCols, j * BKV, bh);
+      }
+    } else if (warp == 2 && lane == 0) {
+      // -------------------------------------------------------------- V producer (the TMEM allocator warp, idle by now)
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        mbar_wait(&v_empty[s], ph ^ 1);
+        uint8_t *vdst = sKV + s * kStageBytes + kKTileBytes;
         mbar_arrive_expect_tx(&v_full[s], kKTileBytes);
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(vdst + c * kKChunkBytes, &tmap_v, &v_full[s], c * kChunkCols, j * BKV, bh);
@@ -187,6 +212,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             umma_ss(tS_i + b * BKV, desc_advance(dsc_q, (k >> 1) * kQChunkBytes + (k & 1) * 32),
                     desc_advance(dk, (k >> 1) * kKChunkBytes + (k & 1) * 32), idesc_qk, k != 0);
           umma_commit(&s_full[i * 2 + b]);
+          umma_commit(&k_empty[s]);                    // K(s) is free once these MMAs have read it
         };
         auto issue_pv = [&](int s, int b, bool accumulate) {
           const uint64_t dv = desc_advance(dsc_v0, s * kStageBytes);
@@ -207,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           mbar_wait(&p_ready[i * 2 + b], (j >> 1) & 1);   // softmax wrote P(j) (and rescaled O if needed)
           tc_fence_after();
           issue_pv(s, b, j > 0);
-          umma_commit(&kv_empty[s]);                   // this stream is done with K(j)/V(j) once PV(j) completes
+          umma_commit(&v_empty[s]);                    // this stream is done with V(j) once PV(j) completes
           if (j + 2 < nkv) {
             const int s2 = (j + 2) % kStages;
             mbar_wait(&k_full[s2], ((j + 2) / kStages) & 1);
@@ -409,15 +435,35 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
     const int v = e ? atoi(e) : 1;
     return (v < 0 || v > 2) ? 1 : v;
   }();
-  MVIT_SMEM_OPT_IN(attn::attention_tc_kernel<0>, attn::kSmemBytes);
-  MVIT_SMEM_OPT_IN(attn::attention_tc_kernel<1>, attn::kSmemBytes);
-  MVIT_SMEM_OPT_IN(attn::attention_tc_kernel<2>, attn::kSmemBytes);
+  // streams per CTA: 2 = one 256-row CTA per SM, 1 = two co-resident 128-row CTAs per SM (see attn::Shape)
+  static const int ns_env = [] {
+    const char *e = getenv("MVIT_ATTN_NS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 1 || v == 2) ? v : 0;
+  }();
+  const int ns = ns_env ? ns_env : 1;
   attn::Params p{static_cast<const bf16 *>(a.q), static_cast<bf16 *>(a.out), a.lse, a.heads, a.Lq, a.Lk, a.add_q,
                  a.scale * 1.44269504088896340736f};
-  dim3 grid((unsigned)((a.Lq + 2 * attn::BQ - 1) / (2 * attn::BQ)), (unsigned)BH);
-  if (poly == 0) attn::attention_tc_kernel<0><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, to, p);
-  else if (poly == 2) attn::attention_tc_kernel<2><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, to, p);
-  else attn::attention_tc_kernel<1><<<grid, attn::kThreads, attn::kSmemBytes, st>>>(tq, tk, tv, to, p);
+  auto go = [&](auto poly_c, auto ns_c) {
+    constexpr int P = decltype(poly_c)::value, NS = decltype(ns_c)::value;
+    using Sh = attn::Shape<NS>;
+    MVIT_SMEM_OPT_IN((attn::attention_tc_kernel<P, NS>), Sh::kSmemBytes);
+    dim3 grid((unsigned)((a.Lq + NS * attn::BQ - 1) / (NS * attn::BQ)), (unsigned)BH);
+    attn::attention_tc_kernel<P, NS><<<grid, Sh::kThreads, Sh::kSmemBytes, st>>>(tq, tk, tv, to, p);
+    return 0;
+  };
+  using std::integral_constant;
+  int rc;
+  if (ns == 1) {
+    rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 1>{})
+       : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 1>{})
+                   : go(integral_constant<int, 1>{}, integral_constant<int, 1>{});
+  } else {
+    rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 2>{})
+       : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 2>{})
+                   : go(integral_constant<int, 1>{}, integral_constant<int, 2>{});
+  }
+  if (rc) return rc;
   MVIT_LAUNCH_OK("attention(tcgen05)");
   return 0;
 }
