@@ -38,6 +38,8 @@ SIGNATURES = {
                                      + [_f, _i, _p]),
     "mvit_attention_pool_qkv_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p]),
     "mvit_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
+    "mvit_attention_rel_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
+    "mvit_relpos_operands_fwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 7 + [_f, _i, _p]),
     "mvit_pos_embed_add": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mvit_mean_head_workspace_floats": (C.c_size_t, [_i, _i, _i]),
     "mvit_mean_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

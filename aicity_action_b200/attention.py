@@ -145,7 +145,8 @@ class MultiScaleAttention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, drop_rate=0.0, kernel_q=(1, 1, 1),
                  kernel_kv=(1, 1, 1), stride_q=(1, 1, 1), stride_kv=(1, 1, 1), norm_layer=nn.LayerNorm,
                  has_cls_embed=True, mode="conv", pool_first=False, use_query_residual_pool=False,
-                 expand_channel=False, expand_to_dim=None):
+                 expand_channel=False, expand_to_dim=None, rel_pos_spatial=False, rel_pos_temporal=False,
+                 rel_pos_zero_init=False, input_size=None):
         super().__init__()
         self.drop_rate = drop_rate
         self.num_heads = num_heads
@@ -191,6 +192,40 @@ class MultiScaleAttention(nn.Module):
         else:
             raise NotImplementedError(f"Unsupported model {mode}")
         self.use_query_residual_pool = use_query_residual_pool
+
+        # Decomposed relative-position bias: a DEFAULT-OFF extension that the reference does not have.
+        # Parameter names / shapes / init follow upstream PySlowFast's MViTv2 (Appendix F): tables shared across heads,
+        # [2*max(q_size, kv_size) - 1, head_dim].  Absent unless requested, so the default state_dict is the reference's.
+        self.rel_pos_spatial, self.rel_pos_temporal = bool(rel_pos_spatial), bool(rel_pos_temporal)
+        if self.rel_pos_spatial or self.rel_pos_temporal:
+            if input_size is None or has_cls_embed or head_dim != 96:
+                raise NotImplementedError("relative-position bias needs input_size=(T,H,W), no cls token and head_dim 96")
+            t, hh, ww = input_size
+            sq = stride_q if len(stride_q) > 0 else (1, 1, 1)
+            skv = stride_kv if len(stride_kv) > 0 else (1, 1, 1)
+            def table(n_q, n_kv):
+                p = nn.Parameter(torch.zeros(2 * max(n_q, n_kv) - 1, head_dim))
+                if not rel_pos_zero_init:
+                    nn.init.trunc_normal_(p, std=0.02)
+                return p
+            self._rel_sizes = ((hh // sq[1], hh // skv[1]), (ww // sq[2], ww // skv[2]), (t // sq[0], t // skv[0]))
+            if self.rel_pos_spatial:                      # upstream creates a table only for the term that is on
+                self.rel_pos_h = table(*self._rel_sizes[0])
+                self.rel_pos_w = table(*self._rel_sizes[1])
+            if self.rel_pos_temporal:
+                self.rel_pos_t = table(*self._rel_sizes[2])
+
+    def _rel_operands(self, q, q_thw, k_thw):
+        """(q_ext, k_ext) of ops.attention(rel=...) or None.  A table that is switched off contributes zeros."""
+        if not (self.rel_pos_spatial or self.rel_pos_temporal):
+            return None
+        tabs = []
+        for name, (nq, nk) in zip(("rel_pos_h", "rel_pos_w", "rel_pos_t"), self._rel_sizes):
+            p = getattr(self, name, None)
+            tabs.append(p if p is not None else torch.zeros(2 * max(nq, nk) - 1, 96, device=q.device))
+        if AG.recording(q, *tabs):
+            raise NotImplementedError("the relative-position bias is a forward-only (eval / no_grad) extension")
+        return ops.relpos_operands(q, q_thw, k_thw, tabs[0], tabs[1], tabs[2], self.scale)
 
     # -- B200 forward ----------------------------------------------------------------------
     def _pooled(self, qkv5, which, pool, norm, thw_shape):
@@ -253,6 +288,8 @@ class MultiScaleAttention(nn.Module):
                                    getattr(self, "norm_k", None), getattr(self, "norm_v", None)) if m is not None
                        for p in m.parameters()]
         if AG.recording(qkv, *pool_params):
+            if self.rel_pos_spatial or self.rel_pos_temporal:
+                raise NotImplementedError("the relative-position bias is a forward-only (eval / no_grad) extension")
             descs, params = self._train_descs()
             if descs is not None:
                 (q, k, v), shapes = AG.pool_qkv(qkv, h, thw_shape, descs, params)
@@ -292,7 +329,8 @@ class MultiScaleAttention(nn.Module):
                 (q, _, _), grids, _ = ops.attention_pool_qkv(qkv, h, list(thw_shape), ws, lns, strides, only=(0,))
                 cur.wait_stream(side)
                 qkv.record_stream(side)
-            return ops.attention(q, k, v, self.scale, self.use_query_residual_pool), grids[0]
+            rel = self._rel_operands(q, grids[0], ops.pooled_thw(list(thw_shape), [3, 3, 3], list(strides[1])))
+            return ops.attention(q, k, v, self.scale, self.use_query_residual_pool, rel=rel), grids[0]
         qkv5 = qkv.view(B, N, 3, h, C // h)
         # the three pooling launches are independent: K and V run on side streams next to Q so the small
         # deep-stage launches overlap instead of queueing (fork / join with events, graph-capturable)
@@ -301,11 +339,12 @@ class MultiScaleAttention(nn.Module):
         fork = torch.cuda.Event()
         fork.record(cur)
         outs = [None, None]
+        k_thw = list(thw_shape)
         for n, (which, pool, norm) in enumerate(((1, self.pool_k, getattr(self, "norm_k", None)),
                                                  (2, self.pool_v, getattr(self, "norm_v", None)))):
             with torch.cuda.stream(side[n]):
                 side[n].wait_event(fork)
-                outs[n], _ = self._pooled(qkv5, which, pool, norm, thw_shape)
+                outs[n], k_thw = self._pooled(qkv5, which, pool, norm, thw_shape)
                 outs[n].record_stream(cur)
         q, out_shape = self._pooled(qkv5, 0, self.pool_q, getattr(self, "norm_q", None), thw_shape)
         for n in range(2):
@@ -313,7 +352,7 @@ class MultiScaleAttention(nn.Module):
         qkv.record_stream(side[0])
         qkv.record_stream(side[1])
         k, v = outs
-        y = ops.attention(q, k, v, self.scale, self.use_query_residual_pool)
+        y = ops.attention(q, k, v, self.scale, self.use_query_residual_pool, rel=self._rel_operands(q, out_shape, k_thw))
         return y, out_shape
 
     def forward(self, x, thw_shape, residual=None, row_scale=None, ln_in=None, want_stats=False):
@@ -343,7 +382,8 @@ class MultiScaleBlock(nn.Module):
                  drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, up_rate=None,
                  kernel_q=(1, 1, 1), kernel_kv=(1, 1, 1), stride_q=(1, 1, 1), stride_kv=(1, 1, 1),
                  mode="conv", has_cls_embed=True, pool_first=False, use_query_residual_pool=False,
-                 channel_expand_front=False, pool_skip_use_conv=False):
+                 channel_expand_front=False, pool_skip_use_conv=False, rel_pos_spatial=False, rel_pos_temporal=False,
+                 rel_pos_zero_init=False, input_size=None):
         super().__init__()
         self.dim = dim
         self.dim_out = dim_out
@@ -361,7 +401,8 @@ class MultiScaleBlock(nn.Module):
             dim, num_heads=num_heads, qkv_bias=qkv_bias, drop_rate=drop_rate, kernel_q=kernel_q,
             kernel_kv=kernel_kv, stride_q=stride_q, stride_kv=stride_kv, norm_layer=nn.LayerNorm,
             has_cls_embed=has_cls_embed, mode=mode, use_query_residual_pool=use_query_residual_pool,
-            expand_channel=self.expand_channel, expand_to_dim=dim_out)
+            expand_channel=self.expand_channel, expand_to_dim=dim_out, rel_pos_spatial=rel_pos_spatial,
+            rel_pos_temporal=rel_pos_temporal, rel_pos_zero_init=rel_pos_zero_init, input_size=input_size)
         if self.expand_channel:
             dim = dim_out
             self.dim = dim_out

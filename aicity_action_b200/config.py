@@ -83,6 +83,8 @@ def get_cfg() -> CfgNode:
                  "POOL_KV_STRIDE_ADAPTIVE": None, "POOL_Q_STRIDE": [], "POOL_KVQ_KERNEL": None,
                  "ZERO_DECAY_POS_CLS": True, "NORM_STEM": False, "SEP_POS_EMBED": False, "DROPOUT_RATE": 0.0,
                  "DIRECT_INPUT": False, "Q_POOL_RESIDUAL": False, "Q_POOL_ALL": False,
+                 # default-off extension, NOT in the reference (upstream PySlowFast names)
+                 "REL_POS_SPATIAL": False, "REL_POS_TEMPORAL": False, "REL_POS_ZERO_INIT": False,
                  "CHANNEL_EXPAND_FRONT": False, "POOL_SKIP_USE_CONV": False, "NO_NORM_BEFORE_AVG": False},
         "DETECTION": {"ENABLE": False, "USE_CUBE_PROP": False, "USE_SPATIAL_MAXPOOL_BEFORE_PROJ": False,
                       "ROI_XFORM_RESOLUTION": 7, "SPATIAL_SCALE_FACTOR": 16, "ALIGNED": True},

@@ -10,6 +10,9 @@ struct AttnArgs {
   int B, heads, Lq, Lk;
   float scale;
   int add_q;
+  // default-off relative-position operand (relpos.cu): [B, heads, L, 64] in the activation dtype;
+  // scores become scale * (q.k + q_ext.k_ext).  Both NULL = the reference's attention.
+  const void *q_ext = nullptr, *k_ext = nullptr;
 };
 
 int attention_simt(const AttnArgs &a, int dtype, cudaStream_t st);

@@ -29,25 +29,33 @@ namespace attn {
 constexpr int BQ = 128, BKV = 64, D = 96;
 constexpr int kChunkCols = 32, kChunks = 3;
 constexpr int kQChunkBytes = BQ * kChunkCols * 2;    // 8 KB: 128 rows x 64 B, SWIZZLE_64B
-constexpr int kQTileBytes = kChunks * kQChunkBytes;  // 24 KB
 constexpr int kKChunkBytes = BKV * kChunkCols * 2;   // 4 KB:  64 rows x 64 B
-constexpr int kKTileBytes = kChunks * kKChunkBytes;  // 12 KB
 // V is staged with a 4th, constant 32-column chunk whose column 0 is all ones: the P·V MMA (N = 112) then also
 // accumulates the softmax denominator l = sum_j P_ij in accumulator column 96 — with exactly the bf16 values the
 // tensor core multiplies, so no row-sum arithmetic is left in the softmax warps.
 constexpr int kVTileBytes = (kChunks + 1) * kKChunkBytes;   // 16 KB
-constexpr int kStageBytes = kKTileBytes + kVTileBytes;      // 28 KB
+constexpr int kRelCols = 64;                         // REL: extra contraction columns of Q and K (see below)
 // Two launch shapes.  NS = 2: one CTA per SM, 256 query rows as two streams sharing every K/V tile, 6-stage ring, all of
 // TMEM.  NS = 1: a 128-row single-stream CTA sized so that TWO are resident per SM (3-stage ring, 256 TMEM columns, 8
 // warps) — each loads its own K/V, but prologue / epilogue / pipeline ramp of one CTA overlap the steady state of the
 // other, which pays when a CTA lives for only ~25 key tiles (Lk = 1568: the fixed cost was ~8 of ~28 us).
-template <int NS> struct Shape {
-  static constexpr int kStages = NS == 2 ? 6 : 3;
+// REL (default-off decomposed relative-position bias; not in the reference): the bias
+// q_i.Rh[h_i,h'_j] + q_i.Rw[w_i,w'_j] + q_i.Rt[t_i,t'_j] is a rank-(k_h+k_w+k_t) product A_i . E_j of per-query tables A
+// and one-hot key indicators E, so it rides in the SAME tensor-core contraction: Q and K carry 64 extra columns
+// (A / scale and E, from relpos.cu) and S = [Q | A/scale] . [K | E]^T needs 10 instead of 6 K16 steps — no bias add in
+// the softmax warps, no [Lq, Lk] tensor.  One CTA per SM (larger Q / K tiles).
+template <int NS, bool REL> struct Shape {
+  static constexpr int kQKChunks = REL ? kChunks + kRelCols / kChunkCols : kChunks;   // 32-column chunks of Q and K: 3 / 5
+  static constexpr int kQTileBytes = kQKChunks * kQChunkBytes;   // 24 / 40 KB
+  static constexpr int kKTileBytes = kQKChunks * kKChunkBytes;   // 12 / 20 KB
+  static constexpr int kStageBytes = kKTileBytes + kVTileBytes;  // 28 / 36 KB
+  static constexpr int kStages = NS == 2 ? (REL ? 4 : 6) : 3;
   static constexpr int kThreads = NS == 2 ? 384 : 256;
   static constexpr int kSmemBytes = NS * kQTileBytes + kStages * kStageBytes + 512 + 1024;
   static constexpr uint32_t kTmemCols = NS == 2 ? 512 : 256;
   static constexpr uint32_t kColO = NS * 128;        // S[i][b] at 128*i + 64*b, O_i at kColO + 112*i
-  static constexpr int kCtasPerSm = NS == 2 ? 1 : 2;
+  static constexpr int kCtasPerSm = (NS == 2 || REL) ? 1 : 2;
+  static_assert(kSmemBytes <= 232448, "shared memory");
 };
 constexpr int DO = D + 16;                           // accumulator columns per stream: 96 outputs + denominator (+pad)
 constexpr uint32_t kColS = 0;
@@ -90,16 +98,20 @@ struct Params {
 };
 
 // POLY: how many of every 4 score pairs take the FMA-pipe exp2 (0 = all MUFU, 1 = 25 %, 2 = 50 %)
-template <int POLY, int NS>
-__global__ void __launch_bounds__(Shape<NS>::kThreads, Shape<NS>::kCtasPerSm)
+template <int POLY, int NS, bool REL>
+__global__ void __launch_bounds__((Shape<NS, REL>::kThreads), (Shape<NS, REL>::kCtasPerSm))
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, Params p) {
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                    const __grid_constant__ CUtensorMap tmap_qe, const __grid_constant__ CUtensorMap tmap_ke, Params p) {
+  using Sh = Shape<NS, REL>;
+  constexpr int kQTileBytes = Sh::kQTileBytes, kKTileBytes = Sh::kKTileBytes, kStageBytes = Sh::kStageBytes;
+  constexpr int kQKChunks = Sh::kQKChunks;
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by an OFFSET in the shared window: the pointer keeps its address space, so every access below compiles
   // to LDS / STS instead of generic LD / ST
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int kStages = Shape<NS>::kStages, kThreads = Shape<NS>::kThreads;
-  constexpr uint32_t kTmemCols = Shape<NS>::kTmemCols, kColO = Shape<NS>::kColO;
+  constexpr int kStages = Sh::kStages, kThreads = Sh::kThreads;
+  constexpr uint32_t kTmemCols = Sh::kTmemCols, kColO = Sh::kColO;
   uint8_t *sQ = smem;                                  // [NS][24 KB]
   uint8_t *sKV = smem + NS * kQTileBytes;              // [stage][K 12 KB | V 12 KB]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + kStages * kStageBytes);
@@ -123,6 +135,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    if constexpr (REL) {
+      tma_prefetch_desc(&tmap_qe);
+      tma_prefetch_desc(&tmap_ke);
+    }
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -168,9 +184,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // -------------------------------------------------------------- TMA producer
       const int ntile = two ? 2 : 1;
       mbar_arrive_expect_tx(q_full, ntile * kQTileBytes);
-      for (int i = 0; i < ntile; ++i)
+      for (int i = 0; i < ntile; ++i) {
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(sQ + i * kQTileBytes + c * kQChunkBytes, &tmap_q, q_full, c * kChunkCols, q0 + i * BQ, bh);
+        if constexpr (REL)
+          for (int c = kChunks; c < kQKChunks; ++c)
+            tma_load_3d(sQ + i * kQTileBytes + c * kQChunkBytes, &tmap_qe, q_full, (c - kChunks) * kChunkCols, q0 + i * BQ, bh);
+      }
       // K ring: a stage is released by the commit that follows QK(j), so K(j+2), K(j+3) stream in while tile j is still
       // in its softmax / PV phase (with K and V released together a 3-stage ring left no slack for the load latency)
       for (int j = 0; j < nkv; ++j) {
@@ -181,6 +201,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_arrive_expect_tx(&k_full[s], kKTileBytes);
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(kdst + c * kKChunkBytes, &tmap_k, &k_full[s], c * kChunkCols, j * BKV, bh);
+        if constexpr (REL)
+          for (int c = kChunks; c < kQKChunks; ++c)
+            tma_load_3d(kdst + c * kKChunkBytes, &tmap_ke, &k_full[s], (c - kChunks) * kChunkCols, j * BKV, bh);
       }
     } else if (warp == 2 && lane == 0) {
       // -------------------------------------------------------------- V producer (the TMEM allocator warp, idle by now)
@@ -189,7 +212,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t ph = (j / kStages) & 1;
         mbar_wait(&v_empty[s], ph ^ 1);
         uint8_t *vdst = sKV + s * kStageBytes + kKTileBytes;
-        mbar_arrive_expect_tx(&v_full[s], kKTileBytes);
+        mbar_arrive_expect_tx(&v_full[s], kChunks * kKChunkBytes);
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(vdst + c * kKChunkBytes, &tmap_v, &v_full[s], c * kChunkCols, j * BKV, bh);
       }
@@ -208,7 +231,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         auto issue_qk = [&](int s, int b) {
           const uint64_t dk = desc_advance(dsc_k0, s * kStageBytes);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k)
+          for (int k = 0; k < kQKChunks * 2; ++k)
             umma_ss(tS_i + b * BKV, desc_advance(dsc_q, (k >> 1) * kQChunkBytes + (k & 1) * 32),
                     desc_advance(dk, (k >> 1) * kKChunkBytes + (k & 1) * 32), idesc_qk, k != 0);
           umma_commit(&s_full[i * 2 + b]);
@@ -406,6 +429,8 @@ bool attention_tc_supported(const AttnArgs &a, const char **why) {
   if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) { *why = "pointers must be 16-byte aligned"; return false; }
   if ((int64_t)a.B * a.heads >= 65536) { *why = "B*heads too large"; return false; }
   if (a.Lq < 1 || a.Lk < 1 || a.B < 1 || a.heads < 1) { *why = "empty problem (Lq, Lk, B, heads must be >= 1)"; return false; }
+  if ((a.q_ext == nullptr) != (a.k_ext == nullptr)) { *why = "q_ext and k_ext must be given together"; return false; }
+  if (a.q_ext && (!al(a.q_ext) || !al(a.k_ext))) { *why = "relative-position operands must be 16-byte aligned"; return false; }
   return true;
 }
 
@@ -444,24 +469,41 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
   const int ns = ns_env ? ns_env : 1;
   attn::Params p{static_cast<const bf16 *>(a.q), static_cast<bf16 *>(a.out), a.lse, a.heads, a.Lq, a.Lk, a.add_q,
                  a.scale * 1.44269504088896340736f};
-  auto go = [&](auto poly_c, auto ns_c) {
+  const bool rel = a.q_ext != nullptr;
+  CUtensorMap tqe = tq, tke = tk;
+  if (rel) {
+    auto enc_ext = [&](CUtensorMap *m, const void *ptr, int L, int box_rows) {
+      const uint64_t dims[3] = {(uint64_t)attn::kRelCols, (uint64_t)L, (uint64_t)BH};
+      const uint64_t strides[2] = {(uint64_t)attn::kRelCols * 2, (uint64_t)L * attn::kRelCols * 2};
+      const uint32_t box[3] = {attn::kChunkCols, (uint32_t)box_rows, 1};
+      return encode_tmap_bf16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    if ((r = enc_ext(&tqe, a.q_ext, a.Lq, attn::BQ))) return r;
+    if ((r = enc_ext(&tke, a.k_ext, a.Lk, attn::BKV))) return r;
+  }
+  auto go = [&](auto poly_c, auto ns_c, auto rel_c) {
     constexpr int P = decltype(poly_c)::value, NS = decltype(ns_c)::value;
-    using Sh = attn::Shape<NS>;
-    MVIT_SMEM_OPT_IN((attn::attention_tc_kernel<P, NS>), Sh::kSmemBytes);
+    constexpr bool REL = decltype(rel_c)::value;
+    using Sh = attn::Shape<NS, REL>;
+    MVIT_SMEM_OPT_IN((attn::attention_tc_kernel<P, NS, REL>), Sh::kSmemBytes);
     dim3 grid((unsigned)((a.Lq + NS * attn::BQ - 1) / (NS * attn::BQ)), (unsigned)BH);
-    attn::attention_tc_kernel<P, NS><<<grid, Sh::kThreads, Sh::kSmemBytes, st>>>(tq, tk, tv, to, p);
+    attn::attention_tc_kernel<P, NS, REL><<<grid, Sh::kThreads, Sh::kSmemBytes, st>>>(tq, tk, tv, to, tqe, tke, p);
     return 0;
   };
   using std::integral_constant;
+  using std::false_type;
+  using std::true_type;
   int rc;
-  if (ns == 1) {
-    rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 1>{})
-       : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 1>{})
-                   : go(integral_constant<int, 1>{}, integral_constant<int, 1>{});
+  if (rel) {          // default-off feature: one tuned shape only
+    rc = go(integral_constant<int, 1>{}, integral_constant<int, 1>{}, true_type{});
+  } else if (ns == 1) {
+    rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 1>{}, false_type{})
+       : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 1>{}, false_type{})
+                   : go(integral_constant<int, 1>{}, integral_constant<int, 1>{}, false_type{});
   } else {
-    rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 2>{})
-       : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 2>{})
-                   : go(integral_constant<int, 1>{}, integral_constant<int, 2>{});
+    rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 2>{}, false_type{})
+       : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 2>{}, false_type{})
+                   : go(integral_constant<int, 1>{}, integral_constant<int, 2>{}, false_type{});
   }
   if (rc) return rc;
   MVIT_LAUNCH_OK("attention(tcgen05)");

@@ -284,6 +284,10 @@ class MViT(nn.Module):
         self._ckpt_decision = {}
 
         self.blocks = nn.ModuleList()
+        rel_sp = bool(cfg.MVIT.get("REL_POS_SPATIAL", False))
+        rel_tm = bool(cfg.MVIT.get("REL_POS_TEMPORAL", False))
+        rel_zero = bool(cfg.MVIT.get("REL_POS_ZERO_INIT", False))
+        blk_thw = list(self.patch_dims)                      # token grid entering block i (for the rel-pos table sizes)
         for i in range(depth):
             num_heads = round_width(num_heads, head_mul[i])
             if self.channel_expand_front:
@@ -298,7 +302,12 @@ class MViT(nn.Module):
                 kernel_kv=pool_kv[i], stride_q=stride_q[i], stride_kv=stride_kv[i], mode=mode,
                 has_cls_embed=self.cls_embed_on, pool_first=pool_first,
                 use_query_residual_pool=self.use_query_residual_pool,
-                channel_expand_front=self.channel_expand_front, pool_skip_use_conv=self.pool_skip_use_conv))
+                channel_expand_front=self.channel_expand_front, pool_skip_use_conv=self.pool_skip_use_conv,
+                # default-off extension (not in the reference): decomposed relative-position bias
+                rel_pos_spatial=rel_sp, rel_pos_temporal=rel_tm, rel_pos_zero_init=rel_zero,
+                input_size=list(blk_thw) if (rel_sp or rel_tm) else None))
+            if len(stride_q[i]) > 0:
+                blk_thw = [n // st for n, st in zip(blk_thw, stride_q[i])]
         embed_dim = dim_out
         self.norm = norm_layer(embed_dim) if not cfg.MVIT.NO_NORM_BEFORE_AVG else None
 

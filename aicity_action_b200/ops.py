@@ -343,9 +343,35 @@ def attention_pool_tokens(x: torch.Tensor, thw: Sequence[int], kernel: Sequence[
     return out, out_thw
 
 
+def relpos_operands(q: torch.Tensor, q_thw: Sequence[int], k_thw: Sequence[int], rel_h: torch.Tensor,
+                    rel_w: torch.Tensor, rel_t: torch.Tensor, scale: float):
+    """Default-off relative-position operands (NOT in the reference): from the pooled, unscaled
+    q [B,h,Lq,96] and the tables rel_pos_h/w/t -> (q_ext [B,h,Lq,64], k_ext [B,h,Lk,64]) for `attention(..., rel=...)`."""
+    global launch_count
+    _need_cuda(q, rel_h, rel_w, rel_t)
+    q = q.contiguous()
+    B, h, Lq, d = q.shape
+    qt, qh, qw = q_thw
+    kt, kh, kw = k_thw
+    assert d == 96 and Lq == qt * qh * qw, "relpos: q must be [B, heads, qt*qh*qw, 96] (no cls token)"
+    assert rel_h.shape == (2 * max(qh, kh) - 1, d) and rel_w.shape == (2 * max(qw, kw) - 1, d) \
+        and rel_t.shape == (2 * max(qt, kt) - 1, d), "relpos: table shapes are [2*max(q,k)-1, 96]"
+    Lk = kt * kh * kw
+    q_ext = torch.empty((B, h, Lq, 64), dtype=q.dtype, device=q.device)
+    k_ext = torch.empty((B, h, Lk, 64), dtype=q.dtype, device=q.device)
+    rh, rw, rt = _f32c(rel_h), _f32c(rel_w), _f32c(rel_t)
+    with _Timed("relpos", 2.0 * B * h * Lq * (kt + kh + kw) * d):
+        check(_lib.load().mvit_relpos_operands_fwd(_ptr(q), _ptr(rh), _ptr(rw), _ptr(rt), _ptr(q_ext), _ptr(k_ext), B * h,
+                                                   qt, qh, qw, kt, kh, kw, float(scale), _dt(q), _stream()),
+              "mvit_relpos_operands_fwd")
+    launch_count += 2
+    return q_ext, k_ext
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, add_q: bool, *,
-              want_lse: bool = False, impl: int = IMPL_AUTO):
-    """q [B,h,Lq,96], k/v [B,h,Lk,96] contiguous -> out [B, Lq, h*96] (+ lse [B,h,Lq] fp32)."""
+              want_lse: bool = False, impl: int = IMPL_AUTO, rel=None):
+    """q [B,h,Lq,96], k/v [B,h,Lk,96] contiguous -> out [B, Lq, h*96] (+ lse [B,h,Lq] fp32).
+    rel = (q_ext, k_ext) from `relpos_operands`: scores = scale*(q·k + q_ext·k_ext) (default-off relative-position bias)."""
     global launch_count
     _need_cuda(q, k, v)
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -354,6 +380,16 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, a
     assert k.shape == (B, h, Lk, d) and v.shape == (B, h, Lk, d) and q.dtype == k.dtype == v.dtype
     out = torch.empty((B, Lq, h * d), dtype=q.dtype, device=q.device)
     lse = torch.empty((B, h, Lq), dtype=torch.float32, device=q.device) if want_lse else None
+    if rel is not None:
+        qe, ke = rel
+        assert qe.shape == (B, h, Lq, 64) and ke.shape == (B, h, Lk, 64) and qe.dtype == q.dtype == ke.dtype
+        assert qe.is_contiguous() and ke.is_contiguous()
+        with _Timed("attention", 4.0 * B * h * Lq * Lk * d + 2.0 * B * h * Lq * Lk * 64):
+            check(_lib.load().mvit_attention_rel_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(qe), _ptr(ke), _ptr(out), _ptr(lse),
+                                                     B, h, Lq, Lk, d, float(scale), 1 if add_q else 0, _dt(q), impl,
+                                                     _stream()), "mvit_attention_rel_fwd")
+        launch_count += 1
+        return (out, lse) if want_lse else out
     with _Timed("attention", 4.0 * B * h * Lq * Lk * d):
         check(_lib.load().mvit_attention_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, h, Lq, Lk, d,
                                              float(scale), 1 if add_q else 0, _dt(q), impl, _stream()),

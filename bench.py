@@ -519,13 +519,15 @@ def run_ours(args):
                 "instrumented_ms_per_step": ms_instr / K}
     # DRAM bytes per attention launch from the committed ncu pass of this same command (profiles/README.md); algorithmic
     # bytes per launch (q, k, v read + out written once) printed beside it
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
-            tr = json.load(f)
-        roofline["traffic"] = tr["avg_dram_bytes_per_launch"]
-        roofline["traffic_source"] = tr["source"]
-    except (OSError, KeyError, ValueError):
-        pass
+    for name in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):       # newest committed capture (tools/ncu_traffic.py)
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f)
+            roofline["traffic"] = tr["avg_dram_bytes_per_launch"]
+            roofline["traffic_source"] = f"profiles/{name} <- {tr['source']}"
+            break
+        except (OSError, KeyError, ValueError):
+            continue
     value = world * B * K / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,

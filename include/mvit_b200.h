@@ -143,6 +143,27 @@ int mvit_attention_fwd(const void *q, const void *k, const void *v, void *out, f
                        int impl, void *stream);
 
 /*
+ * Decomposed relative-position bias (DEFAULT-OFF; north_star item 2).  NOT part of the reference: it follows
+ * upstream PySlowFast's cal_rel_pos_spatial / cal_rel_pos_temporal as restated in SURVEY.md Appendix F and is validated
+ * only against the in-repo restatement (oracle/mvit_oracle.py rel_pos_bias) - parity unpinned.
+ *   scores[i,j] = scale * q_i.k_j + q_i.Rh[h_i,h'_j] + q_i.Rw[w_i,w'_j] + q_i.Rt[t_i,t'_j],  R*[a,b] = rel_pos_*[dist(a,b)],
+ *   dist(a,b) = trunc(a*max(kn/qn,1) - b*max(qn/kn,1) + (kn-1)*max(qn/kn,1))
+ * mvit_relpos_operands_fwd turns q [B*heads, qt*qh*qw, 96] (pooled, normalised, UNscaled) and the fp32 tables
+ * rel_pos_h [2*max(qh,kh)-1, 96], rel_pos_w, rel_pos_t into two 64-column operands in `dtype`:
+ *   q_ext [B*heads, Lq, 64] = [A_h | A_w | A_t | 0] / scale   (A_h[i, h'] = q_i.Rh[h_i, h'] ...)
+ *   k_ext [B*heads, Lk, 64] = one-hot(h'_j) | one-hot(w'_j) | one-hot(t'_j) | 0        (kt + kh + kw <= 64)
+ * and mvit_attention_rel_fwd is mvit_attention_fwd with the contraction extended over them, scores = scale*(q.k + q_ext.k_ext):
+ * the bias rides in the same tensor-core GEMM (10 instead of 6 K16 steps), nothing is added in the softmax and no [Lq, Lk]
+ * tensor exists.  Tokens are ordered (t, h, w), w fastest; no cls token.
+ */
+int mvit_relpos_operands_fwd(const void *q, const float *rel_h, const float *rel_w, const float *rel_t, void *q_ext,
+                             void *k_ext, int BH, int qt, int qh, int qw, int kt, int kh, int kw, float scale, int dtype,
+                             void *stream);
+int mvit_attention_rel_fwd(const void *q, const void *k, const void *v, const void *q_ext, const void *k_ext, void *out,
+                           float *lse, int B, int heads, int Lq, int Lk, int d, float scale, int add_q_residual, int dtype,
+                           int impl, void *stream);
+
+/*
  * Separable positional embedding add (video_model_builder.py:1206-1223):
  *   x[b, (t*HW + s), c] += pos_spatial[s, c] + pos_temporal[t, c]     (in place, fp32 tables)
  * with an optional dtype conversion: `src` (fp32 or bf16 per src_dtype) -> `dst` (dtype).

@@ -14,6 +14,9 @@ those fixtures on every CPU run (the reference tree does not travel to the GPU
 box).  The reference ships no tests of its own, so the fixtures
 generated from its code are the only pin there is.
 
+One function has NO pin: `rel_pos_bias` (the default-off relative-position term of north_star item 2) does not exist
+in the reference and restates upstream PySlowFast from SURVEY.md Appendix F — parity unpinned.
+
 Everything is written functionally over a flat `state_dict` (names/shapes of
 SURVEY.md Appendix B) so the same weights drive the reference, this oracle and
 the CUDA path.  Reference citations are `file:line` under /root/reference.
@@ -212,6 +215,33 @@ POOL_LN_EPS = 1e-5   # attention.py:338 passes the bare nn.LayerNorm
 BLOCK_LN_EPS = 1e-6  # video_model_builder.py:848-850
 
 
+def rel_pos_bias(q: Tensor, q_thw, k_thw, rel_h: Optional[Tensor], rel_w: Optional[Tensor],
+                 rel_t: Optional[Tensor]) -> Tensor:
+    """Decomposed relative-position bias [B, h, Lq, Lk] of upstream PySlowFast's MViTv2 (cal_rel_pos_spatial /
+    cal_rel_pos_temporal).  *** NOT in /root/reference: parity unpinned. ***  Restated from the formula in
+    SURVEY.md Appendix F, in its dense form: gather R[a, b] = table[dist(a, b)], contract with the unscaled pooled q, and
+    broadcast over the axes each term does not depend on.  q: [B, h, qt*qh*qw, d], tokens ordered (t, h, w); no cls."""
+    B, nh, Lq, d = q.shape
+    qt, qh, qw = q_thw
+    kt, kh, kw = k_thw
+    q6 = q.reshape(B, nh, qt, qh, qw, d)
+    bias = q.new_zeros(B, nh, qt, qh, qw, kt, kh, kw)
+
+    def gathered(table, nq, nk):
+        q_ratio, k_ratio = max(nk / nq, 1.0), max(nq / nk, 1.0)
+        dist = torch.arange(nq)[:, None] * q_ratio - torch.arange(nk)[None, :] * k_ratio + (nk - 1) * k_ratio
+        assert table.shape[0] == 2 * max(nq, nk) - 1
+        return table[dist.long()]                                    # [nq, nk, d]
+
+    if rel_h is not None:
+        bias = bias + torch.einsum("bnthwc,hkc->bnthwk", q6, gathered(rel_h, qh, kh))[:, :, :, :, :, None, :, None]
+    if rel_w is not None:
+        bias = bias + torch.einsum("bnthwc,wkc->bnthwk", q6, gathered(rel_w, qw, kw))[:, :, :, :, :, None, None, :]
+    if rel_t is not None:
+        bias = bias + torch.einsum("bnthwc,tkc->bnthwk", q6, gathered(rel_t, qt, kt))[:, :, :, :, :, :, None, None]
+    return bias.reshape(B, nh, Lq, kt * kh * kw)
+
+
 def multiscale_attention(x: Tensor, thw, sd: Dict[str, Tensor], pfx: str, spec: BlockSpec,
                          mvit: MViTSpec, return_parts: bool = False):
     B, N, _ = x.shape
@@ -221,6 +251,7 @@ def multiscale_attention(x: Tensor, thw, sd: Dict[str, Tensor], pfx: str, spec: 
     qkv = qkv.reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)    # :231-236
     parts = []
     out_thw = list(thw)
+    k_thw = list(thw)
     for name, t, kern, strd in (("q", qkv[0], spec.kernel_q, spec.stride_q),
                                 ("k", qkv[1], spec.kernel_kv, spec.stride_kv),
                                 ("v", qkv[2], spec.kernel_kv, spec.stride_kv)):
@@ -234,10 +265,16 @@ def multiscale_attention(x: Tensor, thw, sd: Dict[str, Tensor], pfx: str, spec: 
                                       has_cls=mvit.cls_embed_on, ln=ln)
             if name == "q":
                 out_thw = t_thw
+            elif name == "k":
+                k_thw = t_thw
         parts.append(t)
     q, k, v = parts
     scale = d ** -0.5                                          # :118-119
     attn = (q @ k.transpose(-2, -1)) * scale                   # :267
+    if any(pfx + n in sd for n in ("rel_pos_h", "rel_pos_w", "rel_pos_t")):
+        # default-off extension, absent from the reference (see rel_pos_bias): added to the scaled scores
+        attn = attn + rel_pos_bias(q, out_thw, k_thw, sd.get(pfx + "rel_pos_h"), sd.get(pfx + "rel_pos_w"),
+                                   sd.get(pfx + "rel_pos_t"))
     attn = attn.softmax(dim=-1)                                # :269
     Lq = q.shape[2]
     y = (attn @ v).transpose(1, 2).reshape(B, Lq, C)           # :276

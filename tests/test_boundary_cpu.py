@@ -201,3 +201,19 @@ def test_weight_cache_refreshes_in_place_and_can_be_invalidated():
     c, ct = cached_weight(lin.weight, torch.bfloat16), cached_weight_t(lin.weight, torch.bfloat16)
     assert c.data_ptr() == ptr and torch.equal(c, lin.weight.detach().bfloat16())
     assert ct.data_ptr() == ptr_t and torch.equal(ct, lin.weight.detach().bfloat16().t())
+
+
+def test_rel_pos_is_off_by_default_and_adds_upstream_named_tables_when_on():
+    """The relative-position extension (not in the reference) must not touch the default state_dict."""
+    from aicity_action_b200.config import aicity_cfg
+    from aicity_action_b200.mvit import MViT
+    cfg = aicity_cfg("MVITV2_FULL_B_16x4_CONV.yaml")
+    assert not cfg.MVIT.REL_POS_SPATIAL and not cfg.MVIT.REL_POS_TEMPORAL
+    base = MViT(cfg).state_dict()
+    assert not any("rel_pos" in k for k in base)
+    on = MViT(aicity_cfg("MVITV2_FULL_B_16x4_CONV.yaml", ["MVIT.REL_POS_SPATIAL", True, "MVIT.REL_POS_TEMPORAL", True]))
+    extra = {k: tuple(v.shape) for k, v in on.state_dict().items() if k not in base}
+    assert len(extra) == 3 * len(on.blocks) and set(k.rsplit(".", 1)[1] for k in extra) == {"rel_pos_h", "rel_pos_w", "rel_pos_t"}
+    # block 0 @224: q grid 8x56x56, k/v grid 8x7x7 -> [2*max-1, head_dim]
+    assert extra["blocks.0.attn.rel_pos_h"] == (111, 96) and extra["blocks.0.attn.rel_pos_t"] == (15, 96)
+    assert [k for k in on.state_dict() if k in base] == list(base)       # the reference's keys, in the reference's order

@@ -308,3 +308,43 @@ def test_patch_conv_row_stats():
     tot = st.sum(0)
     bf = b.float().reshape(-1, 96)
     assert rel_inf(tot[:, 0], bf.sum(1)) < 1e-4 and rel_inf(tot[:, 1], (bf * bf).sum(1)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ relative-position bias
+# DEFAULT-OFF extension that the reference does not have: parity here is against the in-repo restatement
+# oracle/mvit_oracle.py::rel_pos_bias of upstream PySlowFast's formula (Appendix F) — unpinned.
+REL_CASES = [
+    # (B, heads, q_thw, k_thw)
+    (1, 2, (2, 8, 8), (2, 8, 8)),            # equal grids
+    (2, 1, (4, 8, 12), (4, 2, 3)),           # K/V pooled 4x (q finer than k)
+    (1, 2, (2, 4, 4), (2, 8, 8)),            # q pooled (q coarser than k)
+    (1, 1, (8, 14, 14), (8, 14, 14)),        # a stage-4 @448 shape: 36 bias columns, ragged tiles
+    (1, 2, (8, 28, 28), (8, 28, 28)),        # 64 bias columns (the maximum)
+]
+
+
+@pytest.mark.parametrize("impl,dtype", [(IMPL_SIMT, torch.float32), (IMPL_SIMT, torch.bfloat16),
+                                        (IMPL_TCGEN05, torch.bfloat16)], ids=["simt-f32", "simt-bf16", "tc-bf16"])
+@pytest.mark.parametrize("B,h,q_thw,k_thw", REL_CASES, ids=str)
+def test_attention_rel_pos(B, h, q_thw, k_thw, impl, dtype):
+    d = 96
+    Lq, Lk = math.prod(q_thw), math.prod(k_thw)
+    q = rounded(synth_input(31, f"rq{q_thw}{k_thw}", (B, h, Lq, d)), dtype)
+    k = rounded(synth_input(32, f"rk{q_thw}{k_thw}", (B, h, Lk, d)), dtype)
+    v = rounded(synth_input(33, f"rv{q_thw}{k_thw}", (B, h, Lk, d)), dtype)
+    tabs = [synth_tensor(34, f"rel{i}", (2 * max(a, b) - 1, d)) * 0.5
+            for i, (a, b) in enumerate(((q_thw[1], k_thw[1]), (q_thw[2], k_thw[2]), (q_thw[0], k_thw[0])))]
+    scale = d ** -0.5
+    bias = O.rel_pos_bias(q, q_thw, k_thw, tabs[0], tabs[1], tabs[2])
+    attn = ((q @ k.transpose(-2, -1)) * scale + bias).softmax(-1)
+    ref = (attn @ v + q).transpose(1, 2).reshape(B, Lq, h * d)
+    qd = dev(q, dtype)
+    rel = ops.relpos_operands(qd, q_thw, k_thw, dev(tabs[0]), dev(tabs[1]), dev(tabs[2]), scale)
+    # the operands themselves: q_ext . k_ext^T * scale == bias
+    got_bias = (rel[0].float() @ rel[1].float().transpose(-2, -1)).cpu() * scale
+    assert rel_inf(got_bias, bias) < TOL[dtype]
+    got = ops.attention(qd, dev(k, dtype), dev(v, dtype), scale, True, impl=impl, rel=rel)
+    assert rel_inf(got, ref) < TOL[dtype], rel_inf(got, ref)
+    # and the bias matters in this test (guards against a silently ignored operand)
+    plain = ops.attention(qd, dev(k, dtype), dev(v, dtype), scale, True, impl=impl)
+    assert rel_inf(plain, ref) > 2 * TOL[dtype]

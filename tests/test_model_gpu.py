@@ -268,3 +268,24 @@ def test_ln_fold_matches_unfolded_and_removes_the_layernorm_launches(c, golden, 
     # each path is within TOL of the fp32 reference, so the two bf16 paths are within 2 TOL of each other
     assert rel_inf(out["1"], out["0"]) < 2 * TOL[torch.bfloat16], (rel_inf(out["1"], ref), rel_inf(out["0"], ref))
     assert launches["0"] - launches["1"] == 2 * len(m.blocks), launches
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("spatial,temporal", [(True, True), (True, False), (False, True)], ids=["st", "s", "t"])
+def test_rel_pos_model_vs_oracle(spatial, temporal, dtype):
+    """MVIT.REL_POS_SPATIAL / REL_POS_TEMPORAL (default off; NOT in the reference): the whole tiny model
+    against the oracle extended with the in-repo restatement of upstream's formula — parity unpinned."""
+    c = MODEL_CASES[0]
+    ov = tiny_cfg_overrides(c) + ["MVIT.REL_POS_SPATIAL", spatial, "MVIT.REL_POS_TEMPORAL", temporal]
+    cfg = aicity_cfg(c["yaml"], ov)
+    m = MViT(cfg).eval()
+    sd = load_synth(m, 77)
+    assert any("rel_pos_h" in k for k in sd) == spatial and any("rel_pos_t" in k for k in sd) == temporal
+    m = m.cuda()
+    x = synth_clip(77, 2, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE)
+    with torch.no_grad():
+        ref = O.mvit_forward(x, sd, O.derive_spec(cfg))
+        got = m([x.cuda().to(dtype)])
+        base = O.mvit_forward(x, {k: v for k, v in sd.items() if "rel_pos" not in k}, O.derive_spec(cfg))
+    assert rel_inf(got, ref) < TOL[dtype], rel_inf(got, ref)
+    assert rel_inf(base, ref) > 1e-3          # the bias changes the output of this model
