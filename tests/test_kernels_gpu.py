@@ -348,3 +348,17 @@ def test_attention_rel_pos(B, h, q_thw, k_thw, impl, dtype):
     # and the bias matters in this test (guards against a silently ignored operand)
     plain = ops.attention(qd, dev(k, dtype), dev(v, dtype), scale, True, impl=impl)
     assert rel_inf(plain, ref) > 2 * TOL[dtype]
+
+
+def test_gelu_epilogue_pointwise_accuracy():
+    """The tcgen05 epilogue's GELU (tanh of a fitted odd polynomial, MUFU) against the exact erf GELU of common.py:20, point by
+    point on [-9, 9]: within the bf16 rounding of the result plus 1e-3 (its documented bound is 3e-4 + 2.5e-4 |x|)."""
+    K = 64
+    x = torch.linspace(-9, 9, 512 * K).reshape(512, K).to(torch.bfloat16)
+    eye = torch.eye(K, dtype=torch.bfloat16)
+    got = ops.linear(x.cuda(), eye.cuda(), None, gelu=True, impl=IMPL_TCGEN05).float().cpu()
+    ref = F.gelu(x.float())
+    err = (got - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 1e-3
+    assert bool((err <= bound).all()), float((err - bound).max())
+    assert float(err.max()) < 2e-2 * float(ref.abs().max())
