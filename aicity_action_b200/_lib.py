@@ -31,6 +31,8 @@ SIGNATURES = {
     "mvit_linear_stat_parts": (_i, [_i64, _i, _i]),
     "mvit_linear_ln_fwd": (_i, [_p, _p, _p, _p, _p, _i, _f, _p, _p, _i64, _p, _p, _i64, _i, _i, _i64, _i64, _i, _p]),
     "mvit_patch_conv_stats_fwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 12 + [_p]),
+    "mvit_mlp_fused_supported": (_i, [_i, _i, _i]),
+    "mvit_mlp_fused_fwd": (_i, [_p, _p, _i, _f, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
     "mvit_im2col3d_fwd": (_i, [_p, _p] + [_i] * 16 + [_p]),
     "mvit_attention_pool_fwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64] + [_i] * 14
                                 + [_f, _i, _p]),

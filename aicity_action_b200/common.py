@@ -66,6 +66,11 @@ class Mlp(nn.Module):
             if ln_in is not None:
                 norm, stats = ln_in
                 wf, bf, colsum = folded_ln_linear(self.fc1.weight, self.fc1.bias, norm.weight, norm.bias)
+                if (residual is x and row_scale is None and ops.mlp_fused_enabled()
+                        and ops.mlp_fused_supported(self.fc1.in_features, self.fc1.out_features, self.fc2.out_features)):
+                    # front stages: fc1 -> GELU -> fc2 -> +x in one kernel, the 4C-wide hidden tile never reaches HBM
+                    return ops.mlp_fused(x, stats, wf, bf, colsum, cached_weight(self.fc2.weight, x.dtype), self.fc2.bias,
+                                         norm.eps)
                 h = ops.linear_ln(x, stats, wf, bf, colsum, norm.eps, gelu=True)
             else:
                 h = AG.linear(x, self.fc1.weight, self.fc1.bias, gelu=True)

@@ -15,15 +15,17 @@ int attention_tc_fault_take();
 int attention_bwd_tc_fault_take();
 int gemm_tc_fault_take();
 int gemm_wgrad_tc_fault_take();
+int pool_tma_fault_take();
+int mlp_fused_fault_take();
 }  // namespace mvit
 
 extern "C" int mvit_abi_version(void) { return 1; }
 extern "C" int mvit_device_fault(void) {
   int n = 0;
-  const char *names[4] = {"attention", "attention_bwd", "linear", "linear_wgrad"};
-  int (*take[4])() = {mvit::attention_tc_fault_take, mvit::attention_bwd_tc_fault_take, mvit::gemm_tc_fault_take,
-                      mvit::gemm_wgrad_tc_fault_take};
-  for (int i = 0; i < 4; ++i) {
+  const char *names[6] = {"attention", "attention_bwd", "linear", "linear_wgrad", "attention_pool", "mlp_fused"};
+  int (*take[6])() = {mvit::attention_tc_fault_take, mvit::attention_bwd_tc_fault_take, mvit::gemm_tc_fault_take,
+                      mvit::gemm_wgrad_tc_fault_take, mvit::pool_tma_fault_take, mvit::mlp_fused_fault_take};
+  for (int i = 0; i < 6; ++i) {
     const int v = take[i]();
     if (v < 0) {
       mvit::set_error("mvit_device_fault: reading the fault flag failed: %s", cudaGetErrorString(cudaGetLastError()));

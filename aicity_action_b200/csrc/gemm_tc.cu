@@ -122,22 +122,8 @@ __device__ __forceinline__ TileCoord conv_tile(const ConvGeom &g, int mt) {
   return c;
 }
 
-// GELU(x) = x * Phi(x) with Phi(x) = 0.5 * (1 + tanh(x * (a1 + a3 x^2))): a1, a3 fitted to the exact (erf) GELU of
-// common.py:20 (max |error| of the fit 2.8e-4 on the whole real line; the textbook tanh-GELU constants give 4.7e-4), tanh on
-// the MUFU pipe (tanh.approx.f32, relative error 2^-11).  Total error <= ~3e-4 + 2.5e-4*|x|, an order of magnitude under
-// the bf16 resolution of the stored activation (2^-9 relative).  5 packed FMA-pipe instructions + 2 MUFU per PAIR of values:
-// the degree-7 erf polynomial it replaces took 11 + 4 clamps, and the fc1 epilogues were bound by exactly those issue slots.
-__device__ __forceinline__ float2 gelu_fast2(float2 x) {
-  const float2 v = __fmul2_rn(x, x);
-  const float2 t = __ffma2_rn(v, make_float2(0.03475185013539659f, 0.03475185013539659f),
-                              make_float2(0.8000458428934369f, 0.8000458428934369f));
-  const float2 g = __fmul2_rn(t, x);
-  float tx, ty;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(g.x));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(g.y));
-  const float2 h = __ffma2_rn(make_float2(tx, ty), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
-  return __fmul2_rn(h, x);
-}
+// forward GELU: tc::gelu_tanh2 (tc_common.cuh)
+__device__ __forceinline__ float2 gelu_fast2(float2 x) { return gelu_tanh2(x); }
 
 // d/dx GELU(x) = Phi(x) + x*phi(x): Phi from the same polynomial, phi(x) = exp(-x^2/2)/sqrt(2 pi) with one MUFU.EX2.
 __device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {

@@ -440,6 +440,9 @@ static int launch(const void *qkv, int B, int heads, int T, int H, int W, const 
 }
 
 }  // namespace ptma
+
+int pool_tma_fault_take() { return tc::tc_fault_take(); }
+
 }  // namespace mvit
 
 // q / k / v of one block.  Tensors whose stride is 1 or 2 go through the TMA kernel (equal strides share a launch); strides

@@ -210,6 +210,40 @@ def linear_ln(x: torch.Tensor, stats: torch.Tensor, w_folded: torch.Tensor, bias
     return y
 
 
+def mlp_fused_enabled() -> bool:
+    """Single-kernel MLP for the C <= 192 blocks on the eval path ($MVIT_B200_MLP_FUSED, default on)."""
+    return os.environ.get("MVIT_B200_MLP_FUSED", "1") not in ("0", "false", "off")
+
+
+def mlp_fused_supported(C: int, H: int, C_out: int) -> bool:
+    return bool(_lib.load().mvit_mlp_fused_supported(int(C), int(H), int(C_out)))
+
+
+def mlp_fused(x: torch.Tensor, stats: torch.Tensor, w1_folded: torch.Tensor, b1_folded: torch.Tensor, colsum1: torch.Tensor,
+              w2: torch.Tensor, b2: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """y = x + fc2(GELU(fc1(LayerNorm(x)))) in one kernel (the hidden activation never reaches HBM); `x` is the raw block
+    stream with row statistics `stats`; the result carries its own row statistics (`row_stats_of`)."""
+    global launch_count
+    _need_cuda(x, stats, w1_folded, b1_folded, colsum1, w2, b2)
+    x = x.contiguous()
+    C = x.shape[-1]
+    H = w1_folded.shape[0]
+    M = x.numel() // C
+    assert x.dtype == torch.bfloat16 and w1_folded.dtype == x.dtype and w2.dtype == x.dtype
+    assert w1_folded.shape == (H, C) and w2.shape == (C, H) and w1_folded.is_contiguous() and w2.is_contiguous()
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and tuple(stats.shape[1:]) == (M, 2)
+    y = torch.empty_like(x)
+    out_stats = torch.empty((1, M, 2), dtype=torch.float32, device=x.device)
+    b2 = _f32c(b2)
+    with _Timed("linear", 4.0 * M * C * H):
+        check(_lib.load().mvit_mlp_fused_fwd(_ptr(x), _ptr(stats), stats.shape[0], float(eps), _ptr(w1_folded), _ptr(b1_folded),
+                                             _ptr(colsum1), _ptr(w2), _ptr(b2), _ptr(y), _ptr(out_stats), M, C, H, _stream()),
+              "mvit_mlp_fused_fwd")
+    launch_count += 1
+    setattr(y, STATS_ATTR, out_stats)
+    return y
+
+
 def attention_pool_strided(src: torch.Tensor, src_offset: int, in_strides: Tuple[int, int, int], B: int,
                            heads: int, d: int, thw: Sequence[int], kernel: Sequence[int],
                            stride: Sequence[int], mode: str, weight: Optional[torch.Tensor],

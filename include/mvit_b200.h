@@ -102,6 +102,19 @@ int mvit_linear_ln_fwd(const void *x, const void *w, const float *bias, const fl
                        int64_t ldr, int epilogue, void *stream);
 
 /*
+ * Fused MLP of a block for the front stages (eval path, bf16, tcgen05 only):
+ *   y = x + fc2(GELU(fc1(LayerNorm(x))))        attention.py:436-445 + common.py:26-33 with norm2 folded as in mvit_linear_ln_fwd
+ * x: RAW block stream [M, C] (also the residual), ln_stats its row statistics [ln_parts][M][2]; w1f = fc1.weight*diag(gamma)
+ * [4C, C] bf16, b1f = fc1.bias + fc1.weight.beta, colsum1[n] = sum_k w1f[n,k]; w2 = fc2.weight [C, 4C] bf16, b2 = fc2.bias.
+ * stats_out (optional) [1][M][2]: row statistics of y for the next block's folded norm1.  The 4C-wide hidden activation stays
+ * in tensor / shared memory.  Supported: C in {96, 192}, hidden = 4C, output width C (mvit_mlp_fused_supported).
+ */
+int mvit_mlp_fused_supported(int C, int H, int C_out);
+int mvit_mlp_fused_fwd(const void *x, const float *ln_stats, int ln_parts, float ln_eps, const void *w1f, const float *b1f,
+                       const float *colsum1, const void *w2, const float *b2, void *y, float *stats_out, int64_t M, int C,
+                       int H, void *stream);
+
+/*
  * im2col for the patch-embedding Conv3d (stem_helper.py:308-338): clip [B, C, T, H, W] (channels-first,
  * as the reference feeds it) -> patch matrix [B*To*Ho*Wo, Kp] with column k = ((c*kt + a)*kh + b)*kw + d
  * (the natural flattening of the Conv3d weight [Cout, C, kt, kh, kw]); zero padding outside the clip and

@@ -362,3 +362,35 @@ def test_gelu_epilogue_pointwise_accuracy():
     bound = ref.abs() * 2.0 ** -8 + 1e-3
     assert bool((err <= bound).all()), float((err - bound).max())
     assert float(err.max()) < 2e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("M,C", [(128, 96), (300, 96), (5000, 96), (40000, 96), (777, 192), (30000, 192)], ids=str)
+def test_mlp_fused(M, C):
+    """mvit_mlp_fused_fwd: y = x + fc2(GELU(fc1(LN(x)))) in one kernel, against the oracle's LayerNorm -> Linear -> GELU ->
+    Linear -> + x on the same bf16 stream, and against the two-GEMM path it replaces; row statistics of the result."""
+    from aicity_action_b200.weights import folded_ln_linear
+    dt = torch.bfloat16
+    H = 4 * C
+    base = rounded(synth_input(41, f"mf{M}{C}", (M, C)) * 1.5 + 0.4, dt)
+    res = rounded(synth_input(42, f"mr{M}{C}", (M, C)), dt)
+    x_dev = ops.linear_stats(dev(base, dt), dev(torch.eye(C) * 0.5, dt), None, residual=dev(res, dt))
+    x = x_dev.float().cpu()
+    stats = ops.row_stats_of(x_dev)
+    w1 = torch.nn.Parameter(synth_tensor(43, f"w1{C}", (H, C)) * C ** -0.5)
+    b1 = torch.nn.Parameter(synth_tensor(43, f"b1{C}", (H,)) * 0.1)
+    w2 = torch.nn.Parameter(synth_tensor(43, f"w2{C}", (C, H)) * H ** -0.5)
+    b2 = torch.nn.Parameter(synth_tensor(43, f"b2{C}", (C,)) * 0.1)
+    g = torch.nn.Parameter(1.0 + 0.3 * synth_tensor(43, f"g{C}", (C,)))
+    be = torch.nn.Parameter(0.2 * synth_tensor(43, f"be{C}", (C,)))
+    ref = (x + F.linear(F.gelu(F.linear(F.layer_norm(x, (C,), g, be, 1e-6), w1, b1)), w2, b2)).detach()
+    wf, bf, cs = folded_ln_linear(w1.cuda(), b1.cuda(), g.cuda(), be.cuda())
+    w2d = w2.detach().cuda().to(dt)
+    assert ops.mlp_fused_supported(C, H, C)
+    got = ops.mlp_fused(x_dev, stats, wf, bf, cs, w2d, b2.detach().cuda(), 1e-6)
+    assert rel_inf(got, ref) < TOL[dt], rel_inf(got, ref)
+    h = ops.linear_ln(x_dev, stats, wf, bf, cs, 1e-6, gelu=True)
+    two = ops.linear(h, w2d, b2.detach().cuda(), residual=x_dev)
+    assert rel_inf(got, two) < TOL[dt]
+    st = ops.row_stats_of(got)
+    gf = got.float()
+    assert st is not None and rel_inf(st[0, :, 0], gf.sum(1)) < 1e-4 and rel_inf(st[0, :, 1], (gf * gf).sum(1)) < 1e-4

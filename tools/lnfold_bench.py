@@ -58,6 +58,18 @@ def main():
             t_ln = timed(lambda: ops.layernorm(xs, g.detach(), be.detach(), 1e-6))
             t_fold = timed(lambda: ops.linear_ln(xs, st, wf, bf, cs, 1e-6, gelu=gelu))
             rows.append(dict(shape=f"{name} {lname} M={M} N={N} K={C}", plain_ms=t_plain, layernorm_ms=t_ln, folded_ms=t_fold))
+        if ops.mlp_fused_supported(C, 4 * C, C):
+            # the whole MLP: folded fc1 + GELU, fc2 + residual + statistics as two launches against the single fused kernel
+            w1 = torch.nn.Parameter(torch.randn(4 * C, C, device="cuda") * C ** -0.5)
+            b1 = torch.nn.Parameter(torch.randn(4 * C, device="cuda") * 0.1)
+            w2 = (torch.randn(C, 4 * C, device="cuda") * (4 * C) ** -0.5).to(dt)
+            b2 = torch.randn(C, device="cuda") * 0.1
+            xs = ops.linear_stats(x, torch.eye(C, device="cuda", dtype=dt), None, residual=res)
+            st = ops.row_stats_of(xs)
+            wf, bf, cs = folded_ln_linear(w1, b1, g, be)
+            t_two = timed(lambda: ops.linear_stats(ops.linear_ln(xs, st, wf, bf, cs, 1e-6, gelu=True), w2, b2, residual=xs))
+            t_fused = timed(lambda: ops.mlp_fused(xs, st, wf, bf, cs, w2, b2, 1e-6))
+            rows.append(dict(shape=f"{name} mlp M={M} C={C}", two_launch_ms=t_two, fused_ms=t_fused))
         for lname, K in (("proj", C), ("fc2", 4 * C)):
             h = torch.randn(M, K, device="cuda", dtype=dt)
             w16 = (torch.randn(C, K, device="cuda") * K ** -0.5).to(dt)
