@@ -122,8 +122,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t *v_empty = k_empty + kStages;   // kStages
   uint64_t *s_full = v_empty + kStages;    // [stream][buffer]
   uint64_t *p_ready = s_full + 4;          // [stream][buffer]
-  uint64_t *o_done = p_ready + 4;          // [stream]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_done + 2);
+  uint64_t *o_done = p_ready + 4;          // [stream][tile parity]: PV(j) commits to o_done[i][j & 1]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_done + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -152,8 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
     }
-    mbar_init(&o_done[0], 1);
-    mbar_init(&o_done[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&o_done[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -237,12 +236,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           umma_commit(&s_full[i * 2 + b]);
           umma_commit(&k_empty[s]);                    // K(s) is free once these MMAs have read it
         };
-        auto issue_pv = [&](int s, int b, bool accumulate) {
+        auto issue_pv = [&](int s, int b, bool accumulate) {   // b = j & 1
           const uint64_t dv = desc_advance(dsc_v0, s * kStageBytes);
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)   // V tile: [64 kv rows][32-col chunk] x3 (+ ones); LBO = chunk stride, SBO = 512
             umma_ts(tO_i, tS_i + b * BKV + k * 8, desc_advance(dv, k * 16 * 64), idesc_pv, (accumulate || k != 0));
-          umma_commit(&o_done[i]);
+          umma_commit(&o_done[i * 2 + b]);
         };
         mbar_wait(q_full, 0);
         for (int jj = 0; jj < 2 && jj < nkv; ++jj) {  // fill both score buffers
@@ -331,7 +330,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           const float m_new = fmaxf(m_used, m_tile);
           const bool need = (m_new - m_used) > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {        // rare (first tiles): rescale O, then redo the pass
-            mbar_wait(&o_done[i], (j - 1) & 1);       // PV(j-1) has landed in O
+            // PV(j-1) has landed in O.  This wait is SKIPPED on most tiles, so the barrier must not be one whose parity a
+            // skipping waiter can alias: with a single o_done barrier flipping every tile (round 1 .. early round 2) every
+            // warp that took this path came out wrong and different from run to run (tools/attn_determinism.py; scores
+            // with a spread of >= 2^8 between key tiles, which trained or transition-block weights produce).  PV(j)
+            // commits to o_done[j & 1], so the barrier waited on here completes every SECOND tile and the waiter is at
+            // most one of ITS phases away from it.
+            mbar_wait(&o_done[i * 2 + (b ^ 1)], ((j - 1) >> 1) & 1);
             tc_fence_after();
             const float alpha = ex2_approx(m_used - m_new);
             m_used = m_new;
@@ -361,7 +366,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_arrive(&p_ready[i * 2 + b]);
       }
       // ---- epilogue: O / l (+ q) -> out[b, row, head*96 + :]
-      mbar_wait(&o_done[i], (nkv - 1) & 1);
+      mbar_wait(&o_done[i * 2 + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1);
       tc_fence_after();
       float l_run;
       {
