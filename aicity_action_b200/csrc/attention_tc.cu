@@ -175,6 +175,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // q / k / v producers have completed (see common.cuh)
+  pdl_launch_dependents();
 
   if (warp < 4) {
     if constexpr (NS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -492,7 +494,8 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
     using Sh = attn::Shape<NS, REL>;
     MVIT_SMEM_OPT_IN((attn::attention_tc_kernel<P, NS, REL>), Sh::kSmemBytes);
     dim3 grid((unsigned)((a.Lq + NS * attn::BQ - 1) / (NS * attn::BQ)), (unsigned)BH);
-    attn::attention_tc_kernel<P, NS, REL><<<grid, Sh::kThreads, Sh::kSmemBytes, st>>>(tq, tk, tv, to, tqe, tke, p);
+    MVIT_CUDA_OK(launch_pdl(attn::attention_tc_kernel<P, NS, REL>, grid, dim3(Sh::kThreads), Sh::kSmemBytes, st, tq, tk, tv, to,
+                            tqe, tke, p));
     return 0;
   };
   using std::integral_constant;

@@ -129,6 +129,44 @@ inline int num_sms() {
   return n;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The forward is a chain of ~170 short dependent kernels.  A kernel launched through launch_pdl() may become resident while
+// its predecessor in the stream is still draining: everything it does before pdl_wait() (shared-memory carve-up, mbarrier
+// init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail; pdl_wait() returns once the predecessor
+// grid has COMPLETED and its writes are visible, so no global memory may be touched before it.  Every kernel launched
+// this way must execute pdl_wait() in all threads that read or write global memory (completion is transitive: a kernel
+// cannot finish before its own wait returned).  pdl_launch_dependents() only allows the next grid to be scheduled early.
+// MVIT_B200_PDL=0 launches the same kernels fully serialised (the wait is then a no-op).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("MVIT_B200_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+// Fills `attr` (room for one more entry at index n) with the PDL attribute when enabled; returns the new count.
+inline int pdl_attr(cudaLaunchAttribute *attr, int n) {
+  if (!pdl_enabled()) return n;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  return n + 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)pdl_attr(attr, 0);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when it is called: do it once
 // per (kernel, device), thread-safe (a bit per device in an atomic mask; a lost race only repeats an idempotent call).
 #define MVIT_SMEM_OPT_IN(kernel, bytes)                                                                          \

@@ -211,6 +211,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // the producer of x / residual / statistics has completed (see common.cuh)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (operands)
@@ -603,18 +605,21 @@ static int launch_tc(const LinearArgs &a, cudaStream_t st) {
   constexpr int TM = PAIR ? 2 * gemm::BM : gemm::BM;
   const int64_t tiles = ((a.M + TM - 1) / TM) * ((a.N + BN - 1) / BN);
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
   if (PAIR) {
     cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(tiles, num_sms() / 2));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    n_attr = 1;
   } else {
     cfg.gridDim = dim3((unsigned)std::min<int64_t>(tiles, num_sms()));
   }
+  n_attr = pdl_attr(attr, n_attr);
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n_attr;
   cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
@@ -664,10 +669,12 @@ int patch_conv_tc(const void *folded, const void *wf, const float *bias, const v
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
   if (stats_out) {
     MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<96, false, gemm::kLnStats>), C::kSmemBytes);
-    gemm::linear_tc_kernel<96, false, gemm::kLnStats><<<grid, C::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+    MVIT_CUDA_OK(launch_pdl(gemm::linear_tc_kernel<96, false, gemm::kLnStats>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st,
+                            tx, tw, ty, tr, p));
   } else {
     MVIT_SMEM_OPT_IN((gemm::linear_tc_kernel<96, false, gemm::kLnNone>), C::kSmemBytes);
-    gemm::linear_tc_kernel<96, false, gemm::kLnNone><<<grid, C::kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tr, p);
+    MVIT_CUDA_OK(launch_pdl(gemm::linear_tc_kernel<96, false, gemm::kLnNone>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st,
+                            tx, tw, ty, tr, p));
   }
   MVIT_LAUNCH_OK("patch_conv(tcgen05)");
   return 0;

@@ -122,6 +122,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  pdl_wait();                 // the producer of x / its row statistics has completed (see common.cuh)
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < G::H; i += kThreads) {
     sB1[i] = p.b1[i];
     sCs[i] = p.colsum[i];
@@ -355,8 +357,7 @@ static int launch(const void *x, const void *w1f, const void *w2, void *y, const
   MVIT_SMEM_OPT_IN(mlp_fused_kernel<C>, G::kSmemBytes);
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const unsigned grid = (unsigned)std::min<int64_t>(m_tiles, num_sms());
-  mlp_fused_kernel<C><<<grid, kThreads, G::kSmemBytes, st>>>(tx, tw1, tw2, ty, p);
-  MVIT_LAUNCH_OK("mlp_fused");
+  MVIT_CUDA_OK(launch_pdl(mlp_fused_kernel<C>, dim3(grid), dim3(kThreads), G::kSmemBytes, st, tx, tw1, tw2, ty, p));
   return 0;
 }
 
