@@ -214,10 +214,13 @@ __global__ void __launch_bounds__(256) fold_clip_kernel(const SRC *__restrict__ 
 // Specialisation of the fold for the MViT patch embedding (C = 3, stride (2,4,4), Cf = 128, bf16 / uint8 sources):
 // compile-time geometry, 16-byte staging loads, one 16-byte store (8 folded channels) per thread.
 // Folded channel ch = ((ot*4 + oh)*4 + ow)*3 + c.
-template <typename SRC, bool FRAMES_U8>
+// TOK = folded tokens (of one image row) per CTA: a whole row where the width allows (112 @448, 56 @224) so that a
+// thread has several independent 16-byte loads in flight before the barrier (with 16-token CTAs the kernel was bound by
+// the latency of one load round per 7 KB of traffic: 0.31 of HBM).
+template <typename SRC, bool FRAMES_U8, int TOK>
 __global__ void __launch_bounds__(256) fold_clip_244x3_kernel(const SRC *__restrict__ x, bf16 *__restrict__ out, int B, int T,
                                                               int H, int W, float mean, float stdv, int strips) {
-  constexpr int C = 3, ST = 2, SH = 4, SW = 4, CF = 128, TOK = kFoldTok;
+  constexpr int C = 3, ST = 2, SH = 4, SW = 4, CF = 128;
   constexpr int ROWS = FRAMES_U8 ? ST * SH : C * ST * SH;          // 8 / 24 staged rows
   constexpr int RL = TOK * SW * (FRAMES_U8 ? C : 1);               // 192 / 64 elements per row
   constexpr int VEC = 16 / (int)sizeof(SRC);                       // elements per 16-byte staging vector
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(256) fold_clip_244x3_kernel(const SRC *__restr
   const int b = bid / Tf;
   const int wf0 = strip * TOK;
   const int ntok = min(TOK, Wf - wf0);
+#pragma unroll 4
   for (int i = threadIdx.x; i < ROWS * RL / VEC; i += 256) {
     const int r = i / (RL / VEC), cv = (i % (RL / VEC)) * VEC;
     const SRC *src;
@@ -248,8 +252,9 @@ __global__ void __launch_bounds__(256) fold_clip_244x3_kernel(const SRC *__restr
     *reinterpret_cast<uint4 *>(&stage[r * RL + cv]) = v;
   }
   __syncthreads();
-  const int tk = threadIdx.x >> 4, v8 = threadIdx.x & 15;          // token, group of 8 folded channels
-  if (tk >= ntok) return;
+  const int v8 = threadIdx.x & 15;                                 // group of 8 folded channels
+#pragma unroll 1
+  for (int tk = threadIdx.x >> 4; tk < ntok; tk += 16) {           // token
   alignas(16) bf16 o[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(256) fold_clip_244x3_kernel(const SRC *__restr
   }
   bf16 *dst = out + ((((int64_t)b * Tf + tf) * Hf + hf) * Wf + wf0 + tk) * CF + v8 * 8;
   *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(o);
+  }
 }
 
 }  // namespace mvit
@@ -382,8 +388,9 @@ extern "C" int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, 
   MVIT_REQUIRE(Cf >= st * sh * sw * C, "fold_clip: Cf too small");
   MVIT_REQUIRE(src_kind >= 0 && src_kind <= 2, "fold_clip: src_kind 0 = f32 [B,C,T,H,W], 1 = bf16 [B,C,T,H,W], 2 = u8 [B,T,H,W,C]");
   if (B == 0) return 0;
-  const int Wf = W / sw, strips = (Wf + kFoldTok - 1) / kFoldTok;
-  const int64_t blocks = (int64_t)B * (T / st) * (H / sh) * strips;
+  const int Wf = W / sw;
+  int strips = (Wf + kFoldTok - 1) / kFoldTok;
+  int64_t blocks = (int64_t)B * (T / st) * (H / sh) * strips;
   MVIT_REQUIRE(blocks < ((int64_t)1 << 31), "fold_clip: grid too large");
   const size_t esz = src_kind == 0 ? 4 : (src_kind == 1 ? 2 : 1);
   const size_t smem = (size_t)C * st * sh * kFoldTok * sw * esz;
@@ -395,10 +402,21 @@ extern "C" int mvit_fold_clip_fwd(const void *clip, int src_kind, void *folded, 
                     (reinterpret_cast<uintptr_t>(clip) & 15) == 0 && (reinterpret_cast<uintptr_t>(folded) & 15) == 0 &&
                     (src_kind == 2 ? (W * 3) % 16 == 0 : W % 8 == 0);
   if (fast) {
-    if (src_kind == 1)
-      fold_clip_244x3_kernel<bf16, false><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const bf16 *>(clip), o, B, T, H, W, mean, stdv, strips);
-    else
-      fold_clip_244x3_kernel<unsigned char, true><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const unsigned char *>(clip), o, B, T, H, W, mean, stdv, strips);
+    const int tok = Wf % 112 == 0 ? 112 : (Wf % 56 == 0 ? 56 : kFoldTok);      // a whole image row per CTA when it divides
+    strips = (Wf + tok - 1) / tok;
+    blocks = (int64_t)B * (T / st) * (H / sh) * strips;
+    const bf16 *cb = static_cast<const bf16 *>(clip);
+    const unsigned char *cu = static_cast<const unsigned char *>(clip);
+    const unsigned nb = (unsigned)blocks;
+    if (src_kind == 1) {
+      if (tok == 112) fold_clip_244x3_kernel<bf16, false, 112><<<nb, 256, 0, s>>>(cb, o, B, T, H, W, mean, stdv, strips);
+      else if (tok == 56) fold_clip_244x3_kernel<bf16, false, 56><<<nb, 256, 0, s>>>(cb, o, B, T, H, W, mean, stdv, strips);
+      else fold_clip_244x3_kernel<bf16, false, kFoldTok><<<nb, 256, 0, s>>>(cb, o, B, T, H, W, mean, stdv, strips);
+    } else {
+      if (tok == 112) fold_clip_244x3_kernel<unsigned char, true, 112><<<nb, 256, 0, s>>>(cu, o, B, T, H, W, mean, stdv, strips);
+      else if (tok == 56) fold_clip_244x3_kernel<unsigned char, true, 56><<<nb, 256, 0, s>>>(cu, o, B, T, H, W, mean, stdv, strips);
+      else fold_clip_244x3_kernel<unsigned char, true, kFoldTok><<<nb, 256, 0, s>>>(cu, o, B, T, H, W, mean, stdv, strips);
+    }
     MVIT_LAUNCH_OK("fold_clip(2,4,4)");
     return 0;
   }

@@ -171,6 +171,49 @@ __global__ void __launch_bounds__(256) maxpool_tokens_bf16_kernel(const bf16 *__
   }
 }
 
+// The shipped geometry (kernel [1,3,3], stride [1,2,2], padding [0,1,1]) without per-element 64-bit index arithmetic:
+// a block owns one output row (b, t, ho), a thread walks its (wo, 16-byte channel vector) slots with 32-bit indices and
+// issues the nine window loads back to back.
+__global__ void __launch_bounds__(256) maxpool_133_s122_bf16_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out,
+                                                                   PoolParams p, int C) {
+  const int vecs = C >> 3;
+  int r = blockIdx.x;
+  const int ho = r % p.Ho; r /= p.Ho;
+  const int t = r % p.T;
+  const int b = r / p.T;
+  const int h0 = 2 * ho - 1;
+  const uint4 *src = reinterpret_cast<const uint4 *>(in + (int64_t)b * p.in_bs) + (int64_t)t * p.H * p.W * vecs;
+  uint4 *dst = reinterpret_cast<uint4 *>(out + (int64_t)b * p.out_bs) + ((int64_t)t * p.Ho + ho) * p.Wo * vecs;
+  const int n = p.Wo * vecs;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int wo = i / vecs, v = i - wo * vecs;
+    const int w0 = 2 * wo - 1;
+    // a tap outside the image is clamped onto the nearest in-image tap OF THE SAME WINDOW, which leaves the maximum
+    // unchanged (the reference pads with -inf): nine unconditional, independent loads
+    uint4 x[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int h = min(max(h0 + a, 0), p.H - 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int w = min(max(w0 + c, 0), p.W - 1);
+        x[a * 3 + c] = __ldg(src + (h * p.W + w) * vecs + v);
+      }
+    }
+    __nv_bfloat162 m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = reinterpret_cast<const __nv_bfloat162 *>(&x[0])[k];
+#pragma unroll
+    for (int q = 1; q < 9; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], reinterpret_cast<const __nv_bfloat162 *>(&x[q])[k]);
+    uint4 o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) reinterpret_cast<__nv_bfloat162 *>(&o)[k] = m[k];
+    dst[i] = o;
+  }
+}
+
 // returns 1 when it does not apply
 static int maxpool_tokens_try(const void *in, void *out, const PoolParams &p, int mode, int dtype, cudaStream_t st) {
   if (mode != MVIT_POOL_MAX || dtype != MVIT_BF16 || p.has_cls || p.has_ln) return 1;
@@ -178,6 +221,13 @@ static int maxpool_tokens_try(const void *in, void *out, const PoolParams &p, in
   // only the plain [B, L, C] -> [B, L', C] layout (heads are consecutive d-channel groups of a token)
   if (p.in_hs != p.d || p.out_hs != p.d || p.in_ls != C || p.out_ls != C || C % 8 != 0) return 1;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (p.in_bs % 8) || (p.out_bs % 8)) return 1;
+  if (p.kt == 1 && p.kh == 3 && p.kw == 3 && p.st == 1 && p.sh == 2 && p.sw == 2 && p.pt == 0 && p.ph == 1 && p.pw == 1 &&
+      (int64_t)p.B * p.T * p.Ho < ((int64_t)1 << 31) && (int64_t)p.H * p.W * (C / 8) < ((int64_t)1 << 31)) {
+    maxpool_133_s122_bf16_kernel<<<(unsigned)(p.B * p.T * p.Ho), 256, 0, st>>>(static_cast<const bf16 *>(in),
+                                                                              static_cast<bf16 *>(out), p, C);
+    MVIT_LAUNCH_OK("attention_pool(maxpool 1x3x3 / 1x2x2)");
+    return 0;
+  }
   const int64_t total = (int64_t)p.B * p.To * p.Ho * p.Wo * (C / 8);
   const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
   maxpool_tokens_bf16_kernel<<<blocks, 256, 0, st>>>(static_cast<const bf16 *>(in), static_cast<bf16 *>(out), p, C);

@@ -166,6 +166,19 @@ def test_attention(B, h, Lq, Lk, dtype):
             assert rel_inf(lse, ref_lse) < 1e-3, (impl, add_q)
 
 
+@pytest.mark.parametrize("B,T,H,W,C", [(2, 4, 14, 14, 192), (1, 2, 7, 9, 96), (3, 1, 28, 28, 768), (1, 3, 5, 1, 32)])
+def test_skip_maxpool_is_exact(B, T, H, W, C):
+    """MaxPool3d([1,3,3],[1,2,2],[0,1,1]) of the skip path (attention.py:427-432) on channels-last tokens: a maximum has no
+    rounding, so the specialised kernel (clamped taps instead of -inf padding) must equal torch bit for bit, odd sizes and
+    single-column images included."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T * H * W, C, generator=g).bfloat16().cuda()
+    got, thw = ops.attention_pool_tokens(x, [T, H, W], [1, 3, 3], [1, 2, 2], mode="max")
+    ref = F.max_pool3d(x.view(B, T, H, W, C).permute(0, 4, 1, 2, 3).float(), (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    assert thw == list(ref.shape[2:])
+    assert torch.equal(got, ref.permute(0, 2, 3, 4, 1).reshape(B, -1, C).bfloat16())
+
+
 @pytest.mark.parametrize("sigma", [2.0, 3.0, 4.0])
 @pytest.mark.parametrize("B,h,Lq,Lk", [(2, 4, 1568, 1568), (1, 2, 6272, 1568), (2, 1, 300, 257)])
 def test_attention_large_score_spread(B, h, Lq, Lk, sigma):
