@@ -131,6 +131,29 @@ def test_attention_bwd(B, h, Lq, Lk, add_q, dtype):
         check(n, a_, r, TOL[dtype])
 
 
+@pytest.mark.parametrize("sigma", [2.0, 3.0])
+@pytest.mark.parametrize("B,h,Lq,Lk", [(1, 2, 784, 784), (2, 1, 1568, 392)])
+def test_attention_bwd_large_score_spread(B, h, Lq, Lk, sigma):
+    """Forward + backward of the fused attention with scores that spread over more than 2^8 between key tiles (the forward's
+    lazy-rescale path; the backward rebuilds P from the saved log-sum-exp): gradients against fp32 autograd on the same bf16
+    values, judged in the 2-norm (peaked softmax rows make single elements of dq/dk ill-conditioned in bf16)."""
+    d = 96
+    g = torch.Generator().manual_seed(13)
+    q, k = (torch.randn(B, h, L, d, generator=g) * sigma for L in (Lq, Lk))
+    v, do = torch.randn(B, h, Lk, d, generator=g), torch.randn(B, Lq, h * d, generator=g)
+    dt = torch.bfloat16
+    qr, kr, vr = (leaf(t.to(dt).double()) for t in (q, k, v))
+    a = ((qr @ kr.transpose(-2, -1)) * d ** -0.5).softmax(-1)
+    y = (a @ vr).transpose(1, 2).reshape(B, Lq, h * d) + qr.transpose(1, 2).reshape(B, Lq, h * d)
+    y.backward(do.to(dt).double())
+    qc, kc, vc = (leaf(t, dt, True) for t in (q, k, v))
+    out = AG.attention(qc, kc, vc, d ** -0.5, True)
+    check("y", out, y, TOL[dt])
+    out.backward(do.cuda().to(dt))
+    for n, a_, r in (("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)):
+        check(n, a_, r, 3e-2, l2=True)
+
+
 @pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
 @pytest.mark.parametrize("thw,sq,skv,heads,pool_q", [((4, 8, 8), (1, 1, 1), (1, 2, 2), 2, True),
                                                       ((4, 8, 8), (1, 2, 2), (1, 4, 4), 1, True),
