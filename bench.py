@@ -578,6 +578,20 @@ def run_ours(args):
             with torch.no_grad():
                 got16 = eval_model([x_cpu.to(dev).bfloat16()]).float().cpu()
                 got32 = eval_model([x_cpu.to(dev)]).float().cpu()
+                # throughput of the fp32 (CUDA-core, 1e-4 parity) path the reference's unmodified scripts land on without
+                # `--compute bf16`: 3 forwards of 2 clips @448 (secondary figure, not the headline)
+                x32 = x_cpu.to(dev).repeat(2, 1, 1, 1, 1)
+                eval_model([x32])
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(3):
+                    eval_model([x32])
+                f1.record()
+                torch.cuda.synchronize()
+                line["inference_fp32"] = {"value": 6.0 / (f0.elapsed_time(f1) * 1e-3), "unit": "clips/s", "batch": 2, "steps": 3,
+                                          "what": "same model, fp32 tensors -> fp32 CUDA-core kernels (MVIT_B200_COMPUTE=auto "
+                                                  "without autocast); the tensor-core path needs bf16 / uint8 input, an "
+                                                  "autocast region or MVIT_B200_COMPUTE=bf16"}
             rel = lambda a: float((a - ref).abs().max() / ref.abs().max())
             line["parity"] = {"against": kind + " (CPU fp32, 1 clip @448, same seeded weights)",
                               "metric": "max|a-b| / max|b| over the class probabilities",

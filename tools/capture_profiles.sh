@@ -13,6 +13,8 @@ for what in attn attn0 gemm_big gemm_gelu gemm_res pool_qkv0 pool_qkv4; do
   timeout 300 ncu --set full --import-source on --clock-control none -s 2 -c 1 -k regex:'attention_tc|linear_tc|pool_tma' \
       -f -o $OUT/prof_${TAG}_${what} python tools/profile_one.py $what > /dev/null 2>&1
 done
+python tools/determinism_probe.py --iters 100 --out $OUT/determinism_${TAG}.json > $OUT/determinism_${TAG}.txt 2>&1
+python tools/attn_determinism.py --runs 10 --out $OUT/attn_determinism_${TAG}.json > $OUT/attn_determinism_${TAG}.txt 2>&1
 python tools/microbench.py --json $OUT/micro_${TAG}_final.json > $OUT/micro_${TAG}_final.txt 2>&1
 python tools/attn_bench.py > $OUT/attn_bench_${TAG}.txt 2>&1
 python tools/lnfold_bench.py $OUT/lnfold_${TAG}.json > $OUT/lnfold_${TAG}.txt 2>&1
