@@ -13,7 +13,8 @@ import csv
 import json
 import sys
 
-FAMILIES = [("attention", "attention_tc_kernel"), ("linear", "linear_tc_kernel"), ("pool_conv", "pool_tma_kernel"),
+FAMILIES = [("attention", "attention_tc_kernel"), ("linear", "linear_tc_kernel"), ("linear", "mlp_fused_kernel"),
+            ("pool_max", "maxpool_"), ("pool_conv", "pool_tma_kernel"),
             ("pool_conv", "pool_tiled_kernel"), ("pool_max", "pool_generic"), ("pool_max", "pool_kernel"),
             ("layernorm", "layernorm"), ("fold_clip", "fold_clip"), ("mean_head", "mean_head")]
 
@@ -35,7 +36,7 @@ def main():
     names = {}
     for r in csv.DictReader(lines):
         per[r["ID"]][r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * \
-            {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3,
+            {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3,
              "second": 1e6}.get(r["Metric Unit"], 1.0)
         names[r["ID"]] = r["Kernel Name"]
     fam = collections.defaultdict(lambda: dict(launches=0, us=0.0, dram_bytes=0.0))
