@@ -97,7 +97,10 @@ struct Params {
   float scale_log2;   // scale * log2(e)
 };
 
-// POLY: how many of every 4 score pairs take the FMA-pipe exp2 (0 = all MUFU, 1 = 25 %, 2 = 50 %)
+// POLY: share of the score pairs whose exp2 runs on the FMA pipe: 0 = none (all MUFU), 3 = 1/8, 1 = 1/4, 2 = 1/2.
+// With two co-resident CTAs per SM (NS = 1) the issue slots the polynomial costs weigh as much as the MUFU cycles it saves:
+// 1/8 is the measured optimum (block-1 shape 1060 TFLOP/s against 1042 / 1010 / 938 at 0 / 1/4 / 1/2); the 256-row
+// one-CTA-per-SM shape of round 1 preferred 1/4.
 template <int POLY, int NS, bool REL>
 __global__ void __launch_bounds__((Shape<NS, REL>::kThreads), (Shape<NS, REL>::kCtasPerSm))
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -318,7 +321,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (e & 1) mx1 = fmaxf(mx1, fmaxf(s0, s1));
             else mx0 = fmaxf(mx0, fmaxf(s0, s1));
             const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
-            const bool poly = POLY == 2 ? (e & 1) == 1 : (POLY == 1 ? (e & 3) == 3 : false);
+            const bool poly = POLY == 2 ? (e & 1) == 1 : (POLY == 3 ? (e & 7) == 7 : (POLY == 1 ? (e & 3) == 3 : false));
             const float2 pe = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
             // bf16 by truncation (one PRMT): numerator and denominator both come from these exact values through
             // the same MMA, so the truncation bias cancels in O / l
@@ -460,12 +463,12 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
     const uint32_t box[4] = {attn::kChunkCols, 1, attn::BQ, 1};
     if ((r = encode_tmap_bf16(&to, a.out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
   }
-  // tuning knob read once (a function-local static is initialised thread-safely); default: a quarter of the
+  // tuning knob read once (a function-local static is initialised thread-safely); default: an eighth of the
   // exponentials on the FMA pipe
   static const int poly = [] {
     const char *e = getenv("MVIT_ATTN_POLY");
-    const int v = e ? atoi(e) : 1;
-    return (v < 0 || v > 2) ? 1 : v;
+    const int v = e ? atoi(e) : 3;
+    return (v < 0 || v > 3) ? 3 : v;
   }();
   // streams per CTA: 2 = one 256-row CTA per SM, 1 = two co-resident 128-row CTAs per SM (see attn::Shape)
   static const int ns_env = [] {
@@ -507,6 +510,7 @@ int attention_tc(const AttnArgs &a, cudaStream_t st) {
   } else if (ns == 1) {
     rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 1>{}, false_type{})
        : poly == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, 1>{}, false_type{})
+       : poly == 3 ? go(integral_constant<int, 3>{}, integral_constant<int, 1>{}, false_type{})
                    : go(integral_constant<int, 1>{}, integral_constant<int, 1>{}, false_type{});
   } else {
     rc = poly == 0 ? go(integral_constant<int, 0>{}, integral_constant<int, 2>{}, false_type{})
