@@ -15,6 +15,8 @@
 //               written back in place -> one elected thread TMA-stores the tile.
 // All global traffic is TMA (fully coalesced, deep memory-level parallelism); the accumulator of tile
 // i+1 is produced while tile i is drained.
+#include <stdlib.h>
+
 #include "linear.cuh"
 #include "tc_common.cuh"
 
@@ -683,6 +685,13 @@ int patch_conv_tc(const void *folded, const void *wf, const float *bias, const v
 // tile configuration: compute-bound shapes (long K): CTA pairs on 256x192 tiles, else 128x128; memory-bound shapes:
 // 128x96 tiles with a deeper output ring
 static int pick_cfg(int64_t M, int N, int K) {
+  static const int forced = [] {
+    const char *e = getenv("MVIT_GEMM_CFG");      // experiments only: force a tile configuration where it is legal
+    return e ? atoi(e) : -1;
+  }();
+  if (forced == 2 && N % 192 == 0) return 2;
+  if (forced == 1 && N % 128 == 0) return 1;
+  if (forced == 0) return 0;
   if (K >= 384 && N % 192 == 0 && ((M + 255) / 256) * (N / 192) >= num_sms() / 2) return 2;
   if (K >= 384 && N % 128 == 0 && ((M + 127) / 128) * (N / 128) >= num_sms()) return 1;
   return 0;
