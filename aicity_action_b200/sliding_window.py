@@ -163,7 +163,8 @@ class SlidingWindowRunner:
     def __init__(self, model: Callable, num_frames: int = 16, sampling_rate: int = 4, proposal_stride: int = 16,
                  batch_size: int = 8, dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
                  rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None,
-                 use_cuda_graph: bool = False, host_threads: int = 3, n_stage: int = 4, device_resize=None):
+                 use_cuda_graph: bool = False, host_threads: Optional[int] = None, n_stage: Optional[int] = None,
+                 device_resize=None):
         self.model, self.T, self.rate = model, num_frames, sampling_rate
         self.length, self.stride = num_frames * sampling_rate, proposal_stride   # run_action...py:76
         self.batch_size, self.dtype, self.device = batch_size, dtype, device
@@ -172,6 +173,13 @@ class SlidingWindowRunner:
         self._graphed = [None, None]
         self._dbuf = [None, None]
         self._copy_stream = None
+        # Host side of the pipeline: worker threads that gather the frames of the next batches into pinned staging.  A batch
+        # of eight 540p windows is ~190 MB of frame copies (~35 ms on one core) against ~12 ms of GPU time, so the default takes
+        # the cores this rank can expect (cores / ranks on the box, one left for the launching thread), between 3 and 8.
+        if host_threads is None:
+            host_threads = min(8, max(3, (os.cpu_count() or 8) // max(1, world) - 1))
+        if n_stage is None:
+            n_stage = host_threads + 1
         self.host_threads, self.n_stage = max(1, host_threads), max(2, n_stage)
         self._stage, self._stage_free = [None], None
         # None: resize on the device whenever the video offers raw frames whose size differs from the model's; True / False force

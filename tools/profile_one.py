@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Launch ONE representative shape of a kernel family a few times (for `ncu -k regex:... -s N -c 1`).
 
-    python tools/profile_one.py attn|gemm_gelu|gemm_res|pool_q|pool_kv|ln
+    python tools/profile_one.py attn|attn0|gemm_big|gemm_gelu|gemm_res|pool_q|pool_kv|pool_qkv0|pool_qkv4|mlp96|mlp192|ln
 Shapes are MViTv2-B 16x4@448 batch-8 stage shapes.
 """
 import os
@@ -49,6 +49,18 @@ elif what in ("pool_qkv0", "pool_qkv4"):       # the fused q+k+v call at the blo
     g, bb = torch.ones(96, device="cuda"), torch.zeros(96, device="cuda")
     st3 = [(1, sq, sq), (1, skv, skv), (1, skv, skv)]
     fn = lambda: ops.attention_pool_qkv(qkv, h, thw, [w] * 3, [(g, bb, 1e-5)] * 3, st3)
+elif what in ("mlp96", "mlp192"):              # the fused MLP of block 0 / blocks 1-2
+    from aicity_action_b200.weights import folded_ln_linear
+    Cc, M = (96, 802816) if what == "mlp96" else (192, 200704)
+    base = torch.randn(M, Cc, device="cuda", dtype=dt)
+    x = ops.linear_stats(base, torch.eye(Cc, device="cuda", dtype=dt), None)
+    stats = ops.row_stats_of(x)
+    w1, b1 = torch.randn(4 * Cc, Cc, device="cuda") * Cc ** -0.5, torch.randn(4 * Cc, device="cuda") * 0.1
+    w2 = (torch.randn(Cc, 4 * Cc, device="cuda") * (4 * Cc) ** -0.5).to(dt)
+    b2 = torch.randn(Cc, device="cuda") * 0.1
+    wf, bf, cs = folded_ln_linear(torch.nn.Parameter(w1), torch.nn.Parameter(b1), torch.nn.Parameter(torch.ones(Cc, device="cuda")),
+                                  torch.nn.Parameter(torch.zeros(Cc, device="cuda")))
+    fn = lambda: ops.mlp_fused(x, stats, wf, bf, cs, w2, b2, 1e-6)
 elif what == "ln":
     x = torch.randn(802816, 96, device="cuda", dtype=dt)
     g, bb = torch.ones(96, device="cuda"), torch.zeros(96, device="cuda")
