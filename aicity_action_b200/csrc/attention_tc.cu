@@ -286,6 +286,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int b = j & 1;
         const uint32_t tS = tS_i + b * BKV;
         mbar_wait(&s_full[i * 2 + b], (j >> 1) & 1);
+        // Observe EVERY phase of o_done[b]: P.V(j-2) was issued before Q.K(j), so this wait returns at once, but it keeps this
+        // thread within one phase of both o_done barriers by its own sequential waits — the rescale path below then waits for
+        // the phase right after the one observed at tile j-1 and its parity test cannot alias, whatever the arrival timing
+        // (compute-sanitizer synccheck flags a barrier that is re-armed without a waiter as "missing wait").
+        if (j >= 2) mbar_wait(&o_done[i * 2 + b], ((j - 2) >> 1) & 1);
         tc_fence_after();
         uint32_t s[2][32];
         tmem_ld32(tS, s[0]);
