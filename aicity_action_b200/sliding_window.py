@@ -69,6 +69,7 @@ class SyntheticVideo:
         self._ramp = torch.arange(h, dtype=torch.int32).view(h, 1, 1)
         self._hw = (h, w)
         self._pool = None
+        self.pinned_store = False          # True: the frame store is pinned and offered to the runner (raw_frames_pinned)
 
     def __len__(self):
         return self.num_frames
@@ -110,6 +111,17 @@ class SyntheticVideo:
         """Native-resolution frames into `out` [n, H, W, 3] (pinned staging); the runner resizes them on the device."""
         torch.index_select(self._textures(), 0, torch.as_tensor([int(i) % self.PERIOD for i in idxs]), out=out)
 
+    def raw_frames_pinned(self):
+        """(frame store [P, H, W, 3] uint8 in PINNED host memory, frame index -> row) when the decoded frames live in pinned
+        memory (a decoder's pinned output ring, a pre-decoded video): the runner then uploads each frame straight from there
+        (one DMA per frame, no staging copy on the host).  None: frames go through `get_raw_into` and the staging ring."""
+        if self.raw_hw is None or not self.pinned_store or not torch.cuda.is_available():
+            return None
+        pool = self._textures()
+        if not pool.is_pinned():
+            self._pool = pool = pool.pin_memory()
+        return pool, (lambda f: int(f) % self.PERIOD)
+
 
 class ArrayVideo:
     """Decoded RGB frames held in host memory ([N, H, W, 3] uint8 array or memmap) — what the reference's decord reader
@@ -127,8 +139,16 @@ class ArrayVideo:
     def get_raw_into(self, idxs: Sequence[int], out: torch.Tensor) -> None:
         """Decoded frames at native resolution into `out` [n, H, W, 3] (pinned staging): the device resizes them."""
         dst = out.numpy()
+        src = self.frames.numpy() if isinstance(self.frames, torch.Tensor) else self.frames
         for n, i in enumerate(idxs):
-            dst[n] = self.frames[int(i)]
+            dst[n] = src[int(i)]
+
+    def raw_frames_pinned(self):
+        """See SyntheticVideo.raw_frames_pinned: offered when `frames` is a pinned uint8 torch tensor."""
+        f = self.frames
+        if isinstance(f, torch.Tensor) and f.dtype == torch.uint8 and f.is_pinned() and f.is_contiguous():
+            return f, int
+        return None
 
     def get_batch(self, idxs: Sequence[int]) -> torch.Tensor:
         import cv2
@@ -164,7 +184,7 @@ class SlidingWindowRunner:
                  batch_size: int = 8, dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
                  rank: int = 0, world: int = 1, group=None, preprocess: Optional[Callable] = None,
                  use_cuda_graph: bool = False, host_threads: Optional[int] = None, n_stage: Optional[int] = None,
-                 device_resize=None):
+                 device_resize=None, direct_upload: Optional[bool] = None):
         self.model, self.T, self.rate = model, num_frames, sampling_rate
         self.length, self.stride = num_frames * sampling_rate, proposal_stride   # run_action...py:76
         self.batch_size, self.dtype, self.device = batch_size, dtype, device
@@ -184,6 +204,9 @@ class SlidingWindowRunner:
         self._stage, self._stage_free = [None], None
         # None: resize on the device whenever the video offers raw frames whose size differs from the model's; True / False force
         self.device_resize = device_resize
+        # None: upload frames straight from a video's pinned frame store when every video of a call offers one
+        # (`raw_frames_pinned`); False: always through get_raw_into + the staging ring
+        self.direct_upload = direct_upload
         self.h2d_bytes = 0                    # bytes uploaded so far (frames + index lists), for the bench's accounting
         if preprocess is None and device is not None and dtype != torch.bfloat16:
             from . import ops
@@ -244,6 +267,9 @@ class SlidingWindowRunner:
                 raise ValueError("local_scores_multi: the videos of one call must share resolution (run them one by one)")
         dev_resize = (self.device_resize is not False and raw_hw is not None and hasattr(v0, "get_raw_into")
                       and (tuple(raw_hw) != (size, size) or self.device_resize is True))
+        stores = [v.raw_frames_pinned() if hasattr(v, "raw_frames_pinned") else None for v in videos] \
+            if (dev_resize and self.direct_upload is not False) else [None]
+        direct = all(st is not None for st in stores)
         shape = (self.batch_size, self.T, size, size, 3)
         nf_max = self.batch_size * self.T
         up_shape = (nf_max,) + tuple(raw_hw) + (3,) if dev_resize else shape
@@ -286,8 +312,18 @@ class SlidingWindowRunner:
                 flat = [f for w in run_ids for f in frame_indices(*windows[w], self.T, len(video))]
                 uniq = sorted(set(flat))
                 pos = {f: n for n, f in enumerate(uniq)}
-                video.get_raw_into(uniq, stage[k][:len(uniq)])
                 stage_idx[k][:len(flat)] = torch.tensor([pos[f] for f in flat], dtype=torch.int32)
+                if direct:
+                    # no host copy: (start row, run length) of the frame store per upload, consecutive rows coalesced
+                    row_of = stores[v][1]
+                    rows, runs = [row_of(f) for f in uniq], []
+                    for r in rows:
+                        if runs and runs[-1][0] + runs[-1][1] == r:
+                            runs[-1][1] += 1
+                        else:
+                            runs.append([r, 1])
+                    return (v, runs), len(run_ids), len(ids), len(uniq)
+                video.get_raw_into(uniq, stage[k][:len(uniq)])
                 return stage[k][:len(uniq)], len(run_ids), len(ids), len(uniq)
             buf = stage[k][:len(run_ids)]
             into = getattr(video, "get_batch_into", None)
@@ -325,13 +361,20 @@ class SlidingWindowRunner:
             with torch.cuda.stream(copy):
                 copy.wait_event(freed[slot])
                 if dev_resize:
-                    draw[slot][:n_uniq].copy_(frames, non_blocking=True)
+                    if direct:
+                        store, n0 = stores[frames[0]][0], 0
+                        for r, ln in frames[1]:
+                            draw[slot][n0:n0 + ln].copy_(store[r:r + ln], non_blocking=True)
+                            n0 += ln
+                    else:
+                        draw[slot][:n_uniq].copy_(frames, non_blocking=True)
                     didx[slot][:n_clips * self.T].copy_(stage_idx[k][:n_clips * self.T], non_blocking=True)
                 else:
                     dev_frames.copy_(frames, non_blocking=True)
                 ready[slot].record(copy)
                 stage_free[k].record(copy)
-            self.h2d_bytes += frames.numel() + (4 * n_clips * self.T if dev_resize else 0)
+            self.h2d_bytes += (n_uniq * draw[slot][0].numel() if (dev_resize and direct) else frames.numel()) \
+                + (4 * n_clips * self.T if dev_resize else 0)
             submit_next()
             cur.wait_event(ready[slot])
             if dev_resize:

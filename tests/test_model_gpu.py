@@ -1,5 +1,6 @@
 """GPU parity of the drop-in modules (MultiScaleAttention / MultiScaleBlock / MViT) against the
 fixtures generated from the unmodified reference and against the CPU oracle."""
+import numpy as np
 import pytest
 import torch
 
@@ -316,3 +317,29 @@ def test_full_model_is_run_to_run_deterministic_and_batch_independent():
             assert torch.equal(m([frames]), first)                # eager == replay
         assert torch.equal(m([frames.flip(0).contiguous()]).flip(0), first)       # batch position
         assert torch.equal(m([frames[:3].contiguous()]), first[:3])               # ragged batch, other batch mates
+
+
+def test_sliding_window_direct_upload_equals_staged():
+    """Frames uploaded straight from a video's pinned frame store (`raw_frames_pinned`, one DMA per frame / run of frames) give
+    the same bits as the staged path (host copy into the pinned ring), for a synthetic store and for a pinned ArrayVideo."""
+    from aicity_action_b200 import sliding_window as SW
+    c = MODEL_CASES[0]
+    cfg = aicity_cfg(c["yaml"], tiny_cfg_overrides(c))
+    m = MViT(cfg).eval()
+    load_synth(m, c["seed"])
+    m = m.cuda()
+    size, T = cfg.DATA.TRAIN_CROP_SIZE, cfg.DATA.NUM_FRAMES
+    kw = dict(num_frames=T, sampling_rate=2, proposal_stride=8, batch_size=3, device=torch.device("cuda"))
+    vid = SW.SyntheticVideo(5, 150, size, raw_hw=(40, 56))
+    staged = SW.SlidingWindowRunner(m, direct_upload=False, **kw).run_video(vid, cfg.MODEL.NUM_CLASSES)
+    vid.pinned_store = True
+    assert vid.raw_frames_pinned() is not None
+    direct = SW.SlidingWindowRunner(m, **kw).run_video(vid, cfg.MODEL.NUM_CLASSES)
+    assert len(staged) == len(direct) and all(a[:2] == b[:2] and np.array_equal(a[2], b[2]) for a, b in zip(staged, direct))
+    # a decoded recording held in pinned memory: consecutive frames coalesce into runs
+    frames = torch.stack([vid.frame(f) for f in range(90)])
+    arr_staged = SW.SlidingWindowRunner(m, **kw).run_video(SW.ArrayVideo(frames.numpy(), size), cfg.MODEL.NUM_CLASSES)
+    pinned = SW.ArrayVideo(frames.pin_memory(), size)
+    assert pinned.raw_frames_pinned() is not None
+    arr_direct = SW.SlidingWindowRunner(m, **kw).run_video(pinned, cfg.MODEL.NUM_CLASSES)
+    assert all(np.array_equal(a[2], b[2]) for a, b in zip(arr_staged, arr_direct))
