@@ -68,7 +68,7 @@ __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, no ran
 }
 
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], rel. error 7.5e-5, far below the
-// bf16 resolution of P): x = n + f, 2^x = 2^f * 2^n with n folded into the exponent bits.  Used for a quarter of
+// bf16 resolution of P): x = n + f, 2^x = 2^f * 2^n with n folded into the exponent bits.  Used for a fraction (POLY) of
 // the score elements so the MUFU pipe stops being the attention bottleneck (SURVEY.md §7 "hard parts").
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   const float2 xc = make_float2(fmaxf(x.x, -120.f), fmaxf(x.y, -120.f));
