@@ -1,20 +1,27 @@
 // Fused pooling attention for sm_100a: out = softmax(q·kᵀ·scale)·v (+ q), head_dim 96, bf16 in/out.
 //
 // Replaces attention.py:267-279 (bmm, *scale, softmax, bmm, transpose/reshape, +q): the [Lq, Lk] score
-// matrix lives only in tensor memory.  One CTA owns 256 query rows of one (batch, head) — two 128-row
-// query tiles ("streams") that share every 64-key K/V tile it loads — and runs five kinds of warps:
-//   warp 0      TMA producer: Q (once) and a 6-stage ring of K/V tiles (64 keys), 64B-swizzled 32-column boxes;
-//   warps 1, 3  MMA issuers, one lane each, one per stream: S = Q·Kᵀ (tcgen05.mma SS, M128 N64 K16 x6) into
-//               one of the stream's TWO score buffers in TMEM, and O += P·V (tcgen05.mma TS: P from TMEM,
-//               V MN-major from smem, N96 K16 x4).  Because S is double-buffered, QKᵀ of tile j+1 is issued
-//               before the softmax of tile j finishes: the softmax warps never wait for the tensor pipe.
-//   warp 2      TMEM allocator (S00 S01 S10 S11 | O0 O1 = 480 of 512 columns); also writes the constant ones chunk;
-//   warps 4-7 / 8-11  softmax of stream 0 / 1: thread = query row (TMEM lane); one pass per tile against the
-//               running (possibly stale) maximum — exp2 domain, 3/4 of the exponentials on MUFU and 1/4 on the
-//               FMA pipe (Cody-Waite + cubic), bf16 packing on the integer pipe, tile maximum reduced on the
-//               side; O is rescaled (and the pass repeated) only when a row maximum grew by more than 2^8.
-//               P (bf16) overwrites the first 32 columns of its score buffer with tcgen05.st.  At the end the
-//               warps normalise O, add the pooled-q residual and store [B, Lq, heads*96] directly.
+// matrix lives only in tensor memory.  Two launch shapes (attn::Shape):
+//   NS = 1 (default): a CTA owns ONE 128-row query tile of one (batch, head) and is sized so that TWO CTAs are resident per
+//           SM (110 KB shared memory, 256 TMEM columns, 8 warps): prologue, pipeline ramp and epilogue of one CTA overlap
+//           the steady state of the other;
+//   NS = 2 (round 1, MVIT_ATTN_NS=2): a CTA owns 256 query rows as two "streams" that share every K/V tile, one CTA per SM.
+// Warps of a CTA (NS = 1; NS = 2 adds a second issuer and a second softmax group):
+//   warp 0      TMA producer: Q (once) and a 3-stage ring of K tiles (64 keys), 64B-swizzled 32-column boxes;
+//   warp 1      MMA issuer, one lane: S = Q·Kᵀ (tcgen05.mma SS, M128 N64 K16 x6) into one of TWO score buffers in TMEM, and
+//               O += P·[V | 1] (tcgen05.mma TS: P from TMEM, V MN-major from smem, N112 K16 x4 — the constant ones column
+//               accumulates the softmax denominator).  Because S is double-buffered, QKᵀ of tile j+1 is issued before the
+//               softmax of tile j finishes;
+//   warp 2      TMEM allocator (S0 S1 | O = 240 of 256 columns), then the TMA producer of the V ring (K and V stages are
+//               released separately);
+//   warps 4-7   softmax: thread = query row (TMEM lane); one pass per tile against the running (possibly stale) maximum —
+//               exp2 domain, 7/8 of the exponentials on MUFU and 1/8 on the FMA pipe (Cody-Waite + cubic), bf16 packing on
+//               the integer pipe, tile maximum reduced on the side; O is rescaled (and the pass repeated) only when a row
+//               maximum grew by more than 2^8 — that path waits for P·V(j-1) on o_done[(j-1) & 1]; every phase of both
+//               o_done barriers is observed by every softmax thread (see the comment at the wait).  P (bf16) overwrites the
+//               first 32 columns of its score buffer with tcgen05.st.  At the end the warps normalise O, add the pooled-q
+//               residual in place over the Q tile in shared memory and one thread TMA-stores [B, Lq, heads*96] directly.
+// Launched with programmatic stream serialisation: everything above pdl_wait() overlaps the previous kernel's drain.
 #include <stdlib.h>
 
 #include <type_traits>
