@@ -13,10 +13,13 @@ JSON line:
   roofline   dominant kernel (fused tcgen05 attention): algorithmic FLOP / CUDA-event time vs the
              measured bf16 peak of MEASURED_PEAKS.json;  `kernels` carries the other kernel families
              (attention_pool in GB/s vs the measured HBM peak, GEMMs in TFLOP/s)
-  cpu_baseline  the CPU oracle port (oracle/mvit_oracle.py, fp32 torch on the host cores) on a bounded
-             sample of the same workload
-`--impl reference` times that CPU port alone (the reference is pure PyTorch-on-CPU for this path and its
-source tree cannot travel to the GPU box; the port is pinned to it bit-for-bit by tests/golden).
+  cpu_baseline  the UNMODIFIED reference (vendored by __graft_entry__.build() into the git-ignored oracle/_ref, which travels
+             to the GPU box) on the host cores, fp32, on a bounded sample of the same workload; the oracle port only if
+             that tree is absent (`kind` says which)
+  parity     the GPU arm (bf16 tcgen05 path and fp32 path) against the probabilities that CPU run just produced
+  sliding_window  BASELINE config 3, sharded w % R with one NCCL all_gather per video, bit-identity against a solo run
+  train      BASELINE config 4 (ACT_CHECKPOINT honoured) and its variants; ddp_grad_check for N > 1
+`--impl reference` times the reference's own CPU implementation alone (rank 0), same metric / config / steps.
 """
 from __future__ import annotations
 
