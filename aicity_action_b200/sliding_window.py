@@ -45,6 +45,17 @@ def frame_indices(t0: int, t1: int, num: int, num_frames: int) -> List[int]:
     return torch.clamp(idx, 0, num_frames - 1).long().numpy().tolist()
 
 
+def coalesce_rows(rows: Sequence[int]) -> List[List[int]]:
+    """[start, length] runs of consecutive rows, in order: the uploads of one batch from a pinned frame store."""
+    runs: List[List[int]] = []
+    for r in rows:
+        if runs and runs[-1][0] + runs[-1][1] == r:
+            runs[-1][1] += 1
+        else:
+            runs.append([int(r), 1])
+    return runs
+
+
 def shard_windows(n_windows: int, rank: int, world: int) -> List[int]:
     """Round-robin deal: window w belongs to rank w % world."""
     return list(range(rank, n_windows, world))
@@ -316,13 +327,7 @@ class SlidingWindowRunner:
                 if direct:
                     # no host copy: (start row, run length) of the frame store per upload, consecutive rows coalesced
                     row_of = stores[v][1]
-                    rows, runs = [row_of(f) for f in uniq], []
-                    for r in rows:
-                        if runs and runs[-1][0] + runs[-1][1] == r:
-                            runs[-1][1] += 1
-                        else:
-                            runs.append([r, 1])
-                    return (v, runs), len(run_ids), len(ids), len(uniq)
+                    return (v, coalesce_rows([row_of(f) for f in uniq])), len(run_ids), len(ids), len(uniq)
                 video.get_raw_into(uniq, stage[k][:len(uniq)])
                 return stage[k][:len(uniq)], len(run_ids), len(ids), len(uniq)
             buf = stage[k][:len(run_ids)]

@@ -217,3 +217,35 @@ def test_rel_pos_is_off_by_default_and_adds_upstream_named_tables_when_on():
     # block 0 @224: q grid 8x56x56, k/v grid 8x7x7 -> [2*max-1, head_dim]
     assert extra["blocks.0.attn.rel_pos_h"] == (111, 96) and extra["blocks.0.attn.rel_pos_t"] == (15, 96)
     assert [k for k in on.state_dict() if k in base] == list(base)       # the reference's keys, in the reference's order
+
+
+def test_pdl_launched_kernels_wait_on_their_predecessor():
+    """A kernel launched with programmatic stream serialisation that never executes griddepcontrol.wait would run
+    concurrently with the producer of its inputs.  Every kernel family that `launch_pdl` / `pdl_attr` launches must carry the
+    wait (SASS: ACQBULK) and the early-launch trigger (PREEXIT) in every instantiation, and no other source may use them."""
+    import glob
+    import re
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "aicity_action_b200", "lib", "libmvit_b200.so")
+    if shutil.which("cuobjdump") is None or not os.path.exists(lib):
+        pytest.skip("cuobjdump or the built library is not available")
+    users = sorted(os.path.basename(f) for f in glob.glob(os.path.join(ROOT, "aicity_action_b200", "csrc", "*.cu"))
+                   if re.search(r"\blaunch_pdl\(|\bpdl_attr\(", open(f).read()))
+    assert users == ["attention_tc.cu", "gemm_tc.cu", "mlp_fused.cu"], users
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    waits, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            waits.setdefault(fn, [0, 0])
+        elif fn and "ACQBULK" in line:
+            waits[fn][0] += 1
+        elif fn and "PREEXIT" in line:
+            waits[fn][1] += 1
+    families = ("attention_tc_kernel", "linear_tc_kernel", "mlp_fused_kernel")
+    checked = [f for f in waits if any(k in f for k in families)]
+    assert len(checked) >= 15
+    for f in checked:
+        assert waits[f][0] >= 1 and waits[f][1] >= 1, f

@@ -164,3 +164,18 @@ def test_merge_prefers_longest_view_and_bankers_rounding():
     # at least 3 of them lie in [10, 20): blocks 12..20 = frames [192, 336); the closing frame 336 belongs to the chunk
     start, end = out[0][2], out[0][3]
     assert (start, end) == (round(192 / 30.0) + 1.0, round(336 / 30.0) - 1.0) == (7.0, 10.0)
+
+
+def test_coalesce_rows_covers_every_row_once_in_order():
+    """Uploads of a batch from a pinned frame store: runs of consecutive rows, order kept (the device index list refers to
+    positions in this order), wrap-around of a periodic store starts a new run."""
+    import random
+    from aicity_action_b200.sliding_window import coalesce_rows
+    assert coalesce_rows([]) == []
+    assert coalesce_rows([3, 4, 5, 9, 10, 0, 1]) == [[3, 3], [9, 2], [0, 2]]
+    assert coalesce_rows([7, 7, 8]) == [[7, 1], [7, 2]]
+    rng = random.Random(0)
+    for _ in range(50):
+        rows = [rng.randrange(40) for _ in range(rng.randrange(1, 60))]
+        flat = [r0 + k for r0, n in coalesce_rows(rows) for k in range(n)]
+        assert flat == rows
